@@ -1,0 +1,251 @@
+/*
+ * selfplay_b200.h — C ABI of the B200-native self-play engine.
+ *
+ * This is the drop-in boundary for the reference's self-play hot path
+ * (joshua16266261/self-play-ai): src/mcts.rs (Mcts::search, Tree, use_subtree),
+ * src/game/{mod,connect_four,tictactoe}.rs (State / Policy traits) and
+ * src/model/mod.rs (Model::predict / Net::forward).  The reference has no FFI
+ * of its own (100 % safe Rust); a Rust `-sys` crate binds exactly these symbols
+ * (see INTEGRATION.md and rust/selfplay-b200-sys/).  Every entry point cites the
+ * reference interface it replaces as `ref: file:line`.
+ *
+ * Conventions
+ *   - every function returns int32_t: 0 = SPB_OK, negative = error.  The text of
+ *     the last error on a handle is spb_last_error(handle) (spb_last_error(NULL)
+ *     returns the text of the last spb_create failure on this thread).
+ *   - no panics / aborts cross the ABI; node-pool exhaustion is SPB_ERR_POOL.
+ *   - the caller owns every buffer it passes; pointers are HOST pointers unless
+ *     the parameter name ends in `_dev`.
+ *   - a handle is NOT thread-safe: one handle per host thread per GPU, which is
+ *     how the reference uses one `Mcts` per worker thread (ref: main.rs:169).
+ *   - there is no CPU fallback: spb_create fails with SPB_ERR_CUDA when no
+ *     sm_100 device is present.
+ */
+#ifndef SELFPLAY_B200_H
+#define SELFPLAY_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPB_ABI_VERSION 1
+
+/* ---- status codes ------------------------------------------------------- */
+#define SPB_OK             0
+#define SPB_ERR_ARG       -1   /* bad argument (null pointer, slot out of range, ...) */
+#define SPB_ERR_CUDA      -2   /* CUDA runtime error / no sm_100 device */
+#define SPB_ERR_POOL      -3   /* a tree's node pool is full (max_nodes_per_tree) */
+#define SPB_ERR_ILLEGAL   -4   /* illegal move / game already ended (ref: connect_four.rs:193,209) */
+#define SPB_ERR_WEIGHTS   -5   /* weight blob malformed / tensor missing / shape mismatch */
+#define SPB_ERR_STATE     -6   /* call not valid in the engine's current state */
+#define SPB_ERR_NOMEM     -7   /* host or device allocation failed */
+
+/* ---- games (ref: src/game/mod.rs:1-3) ----------------------------------- */
+#define SPB_GAME_TICTACTOE 0   /* ref: src/game/tictactoe.rs   A = 9, board 3x3 */
+#define SPB_GAME_CONNECT4  1   /* ref: src/game/connect_four.rs A = 7, board 6x7 */
+#define SPB_MAX_ACTIONS    9
+
+/* ---- Status (ref: src/game/mod.rs:9-15) --------------------------------- */
+#define SPB_STATUS_ONGOING 0
+#define SPB_STATUS_TIED    1
+#define SPB_STATUS_WON     2
+
+/* ---- evaluators --------------------------------------------------------- */
+#define SPB_EVAL_NET       0   /* fused bf16 tcgen05 conv ResNet (ref: model/connect_four.rs:50-81) */
+#define SPB_EVAL_DET       1   /* deterministic hash evaluator, SURVEY.md §8(c) — parity harness */
+#define SPB_EVAL_UNIFORM   2   /* raw p = 1.0 for every action, v = 0 — parity harness */
+
+/*
+ * A game position.  Replaces `State` (ref: connect_four.rs:20-26, tictactoe.rs:20-26):
+ * board + current_player + num_actions_played + status.
+ *   Connect4   : bit (col*7 + row) of stones[p], row 0 = bottom (ref: connect_four.rs:17-18, :52-65)
+ *   Tic-tac-toe: bit (row*3 + col) of stones[p]
+ * stones[0] = Player::X (moves first), stones[1] = Player::O.
+ */
+typedef struct spb_state {
+  uint64_t stones[2];
+  uint8_t  current_player;      /* 0 = X, 1 = O        (ref: connect_four.rs:23)  */
+  uint8_t  num_actions_played;  /*                     (ref: connect_four.rs:24)  */
+  uint8_t  status;              /* SPB_STATUS_*        (ref: connect_four.rs:25)  */
+  uint8_t  reserved[5];         /* must be zero */
+} spb_state;
+
+/*
+ * Engine configuration.  Mirrors the fields of `Args` that the hot path reads
+ * (ref: mcts.rs:8-18): `c` (read from the Tree, mcts.rs:99, default 2.0 mcts.rs:49).
+ * `num_searches` is an argument of spb_search.
+ */
+typedef struct spb_config {
+  uint32_t abi_version;          /* SPB_ABI_VERSION */
+  int32_t  game;                 /* SPB_GAME_* */
+  int32_t  device;               /* CUDA device ordinal */
+  uint32_t num_games;            /* G: concurrent trees ("slots"); ref: mcts.rs:54 num_parallel_self_play_games */
+  uint32_t max_nodes_per_tree;   /* arena capacity per tree; 0 = default (16384) */
+  uint32_t leaves_per_tree;      /* K in-flight leaves per tree per step; 1 = the reference algorithm */
+  float    c;                    /* PUCT constant; ref: mcts.rs:49 (2.0) */
+  int32_t  evaluator;            /* SPB_EVAL_* */
+  uint32_t flags;                /* SPB_FLAG_* */
+  uint32_t reserved[7];          /* must be zero */
+} spb_config;
+
+#define SPB_FLAG_NO_GRAPH   1u   /* launch kernels directly instead of through a CUDA graph */
+#define SPB_FLAG_EVAL_SIMT  2u   /* use the CUDA-core evaluator kernel instead of tcgen05 (debug / cross-check) */
+
+typedef struct spb_engine spb_engine;
+
+/* Exact integer counters; feed the roofline formulas of SURVEY.md §8(d). */
+typedef struct spb_counters {
+  uint64_t simulations;          /* iterations of mcts.rs:214 summed over trees */
+  uint64_t evaluations;          /* leaves sent to the evaluator (mcts.rs:268) */
+  uint64_t terminal_leaves;      /* simulations that ended on a terminal node (mcts.rs:245) */
+  uint64_t path_length_sum;      /* sum over simulations of select() calls (mcts.rs:239-241) */
+  uint64_t children_created;     /* nodes appended by expand (mcts.rs:116-143) */
+  uint64_t nodes_live;           /* sum of arena lengths over slots, now */
+  uint64_t kernel_launches;      /* kernels of this library launched since create/reset_counters */
+  uint64_t reserved[5];
+} spb_counters;
+
+/* ---- lifecycle ---------------------------------------------------------- */
+
+/* Fill `cfg` with defaults: Connect4, device 0, 100 games (mcts.rs:54), c = 2.0, K = 1, SPB_EVAL_NET. */
+int32_t spb_default_config(spb_config* cfg);
+
+/* ref: Mcts{args, model} construction, main.rs:43-44 / learner_concurrent.rs:30-34. */
+int32_t spb_create(const spb_config* cfg, spb_engine** out);
+int32_t spb_destroy(spb_engine* e);
+const char* spb_last_error(const spb_engine* e);
+int32_t spb_abi_version(void);
+
+/* ---- weights (ref: VarStore::save learner.rs:192, ::load main.rs:61) ----- */
+
+/*
+ * Load a safetensors blob exported from the reference's VarStore.  BatchNorm (eval
+ * mode, eps 1e-5) is folded into the preceding conv, weights are cast to bf16 and
+ * packed into the evaluator's shared-memory layout.  Tensors are matched by
+ * creation order of model/connect_four.rs:50-73 (see INTEGRATION.md for the name table).
+ */
+int32_t spb_load_weights(spb_engine* e, const void* safetensors_blob, size_t num_bytes);
+
+/* ---- trees (ref: Tree::default mcts.rs:67, Tree::with_root_state mcts.rs:86) ---- */
+
+/*
+ * (Re)start the trees in `slots[0..n)` from `roots[i]`; roots == NULL means the
+ * default state (empty board, X to move).  slots == NULL means slots 0..n-1.
+ */
+int32_t spb_reset_games(spb_engine* e, const uint32_t* slots, uint32_t n, const spb_state* roots);
+
+/*
+ * ref: Mcts::search mcts.rs:196-332.  Runs `num_searches` lock-step simulations
+ * (mcts.rs:214) for every slot.  Statistics accumulate on top of whatever the tree
+ * already holds (subtree reuse, mcts.rs:161-192).
+ */
+int32_t spb_search(spb_engine* e, uint32_t num_searches);
+
+/*
+ * ref: mcts.rs:310-331 — the second element of search()'s result for one tree:
+ * for each root child in child (= legal action) order: action taken, visit count,
+ * arena id.  Any output pointer may be NULL.  Arrays need SPB_MAX_ACTIONS entries.
+ */
+int32_t spb_root_children(spb_engine* e, uint32_t slot, uint8_t* actions,
+                          uint32_t* visit_counts, uint32_t* child_ids, uint32_t* n_children);
+
+/*
+ * Batched form for all G slots in one device->host copy.  Row i belongs to slot i;
+ * visit_counts / child_ids are [G][SPB_MAX_ACTIONS] indexed by CHILD ORDER,
+ * actions likewise; n_children is [G].
+ */
+int32_t spb_root_children_all(spb_engine* e, uint8_t* actions, uint32_t* visit_counts,
+                              uint32_t* child_ids, uint32_t* n_children);
+
+/*
+ * ref: mcts.rs:315-328 — the first element of search()'s result: root child visit
+ * counts scattered by action then divided by their sum (f32).  `policy` has A floats
+ * (7 for Connect4, 9 for tic-tac-toe, row-major).
+ */
+int32_t spb_root_policy(spb_engine* e, uint32_t slot, float* policy);
+
+/*
+ * ref: Tree::use_subtree mcts.rs:161-192.  Re-roots slot[i] at arena node
+ * node_ids[i] (BFS compaction that keeps visit_count / value_sum / prior and child
+ * order).  out_states (nullable) receives the new root state of each slot.
+ */
+int32_t spb_advance(spb_engine* e, const uint32_t* slots, const uint32_t* node_ids,
+                    uint32_t n, spb_state* out_states);
+
+/* ref: `tree.arena[id].state` (learner_concurrent.rs:184,195; main.rs:92). */
+int32_t spb_get_state(spb_engine* e, uint32_t slot, uint32_t node_id, spb_state* out);
+
+/* ref: `tree.arena.len()`; also the per-node statistics the reference keeps private (mcts.rs:26-29). */
+int32_t spb_arena_len(spb_engine* e, uint32_t slot, uint32_t* out);
+int32_t spb_node_stats(spb_engine* e, uint32_t slot, uint32_t node_id, uint32_t* visit_count,
+                       float* value_sum, float* prior, uint32_t* first_child, uint32_t* n_children);
+
+/* ---- evaluator at the predict boundary (ref: Model::predict model/mod.rs:36-98) ---- */
+
+/*
+ * Evaluates `n` states: policies[n][A] = softmax(logits) masked by legal moves and
+ * renormalised (connect_four.rs:261-279), values[n].  With SPB_EVAL_NET this is the
+ * fused conv ResNet; raw_logits (nullable, [n][A]) receives the pre-softmax logits
+ * (Net::forward, model/connect_four.rs:75-81).
+ */
+int32_t spb_predict(spb_engine* e, const spb_state* states, uint32_t n,
+                    float* policies, float* values, float* raw_logits);
+
+/* ---- game rules, batched on the device (ref: State trait game/mod.rs:21-33) ---- */
+
+/* get_next_state (connect_four.rs:190-211 / tictactoe.rs:135-167).  err[i] = 0 or SPB_ERR_ILLEGAL. */
+int32_t spb_game_next_states(spb_engine* e, const spb_state* states, const uint8_t* actions,
+                             uint32_t n, spb_state* out_states, int32_t* err);
+/* get_valid_actions (connect_four.rs:213-225): bit a of masks[i] set = action a legal. */
+int32_t spb_game_valid_actions(spb_engine* e, const spb_state* states, uint32_t n, uint32_t* masks);
+/* get_encoding (connect_four.rs:242-259): out[n][3][rows][cols] f32. */
+int32_t spb_game_encode(spb_engine* e, const spb_state* states, uint32_t n, float* out);
+
+/* ---- self-play driver (ref: SelfPlayWorker::self_play learner_concurrent.rs:169-242) ---- */
+
+#define SPB_MOVE_GREEDY_LAST_MAX 0  /* ref: main.rs:108-112 (arg-max visit count, last max wins) */
+#define SPB_MOVE_TEMPERATURE     1  /* ref: learner_concurrent.rs:189-194 (sample ∝ N^temperature), counter-based RNG */
+
+/* One finished-or-not position record of a trajectory (compact 48-byte form). */
+typedef struct spb_position {
+  uint64_t stones[2];            /* position the search was run from (root state) */
+  uint32_t visit_counts[7];      /* root child visit counts scattered BY ACTION (Connect4: column) */
+  uint8_t  current_player;
+  uint8_t  ply;                  /* index of this position inside its game */
+  int8_t   outcome;              /* value target for this position: +1 / 0 / -1 (learner_concurrent.rs:214-226) */
+  uint8_t  reserved;
+} spb_position;                  /* 48 bytes */
+
+/*
+ * One self-play ply for every live slot, entirely on the device: pick a child of
+ * the root by `rule`, record (root state, visit counts), then either finish the
+ * game (terminal child: emit the trajectory with outcomes, restart the slot from
+ * a fresh root if `restart_roots` != NULL, else leave it idle) or re-root
+ * (use_subtree).  `seed` feeds the counter-based RNG of SPB_MOVE_TEMPERATURE.
+ * n_finished (nullable) receives the number of games that ended in this call.
+ */
+int32_t spb_selfplay_step(spb_engine* e, int32_t rule, float temperature, uint64_t seed,
+                          const spb_state* restart_roots, uint32_t* n_finished);
+
+/* Copies finished positions (ordered by game sequence number, then ply) to `buf`. */
+int32_t spb_drain_trajectories(spb_engine* e, spb_position* buf, size_t capacity, size_t* written,
+                               uint64_t* game_ids /* nullable, [capacity] global game id per position */);
+
+/* ---- counters / timing -------------------------------------------------- */
+int32_t spb_get_counters(spb_engine* e, spb_counters* out);
+int32_t spb_reset_counters(spb_engine* e);
+/*
+ * Device time (CUDA events on the engine's stream) of the most recent spb_search,
+ * and of the evaluator kernel launches inside it (sum, count).
+ */
+int32_t spb_last_search_timing(spb_engine* e, float* search_ms, float* evaluator_ms,
+                               uint32_t* evaluator_launches);
+int32_t spb_synchronize(spb_engine* e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SELFPLAY_B200_H */
