@@ -88,11 +88,15 @@ typedef struct spb_config {
   float    c;                    /* PUCT constant; ref: mcts.rs:49 (2.0) */
   int32_t  evaluator;            /* SPB_EVAL_* */
   uint32_t flags;                /* SPB_FLAG_* */
-  uint32_t reserved[7];          /* must be zero */
+  uint32_t game_id_base;         /* id of slot 0's first self-play game (rank offset when games are sharded over GPUs) */
+  uint32_t game_id_stride;       /* id increment when a slot starts its next game; 0 = num_games */
+  uint32_t reserved[5];          /* must be zero */
 } spb_config;
 
 #define SPB_FLAG_NO_GRAPH   1u   /* launch kernels directly instead of through a CUDA graph */
 #define SPB_FLAG_EVAL_SIMT  2u   /* use the CUDA-core evaluator kernel instead of tcgen05 (debug / cross-check) */
+#define SPB_FLAG_FORCE_SPLIT 4u  /* run DetEval / uniform through the lock-step select -> evaluate -> expand pipeline
+                                    of the network evaluator instead of the fused single-kernel search */
 
 typedef struct spb_engine spb_engine;
 
@@ -128,6 +132,12 @@ int32_t spb_abi_version(void);
  * creation order of model/connect_four.rs:50-73 (see INTEGRATION.md for the name table).
  */
 int32_t spb_load_weights(spb_engine* e, const void* safetensors_blob, size_t num_bytes);
+
+/*
+ * Host-only validation of a checkpoint (no GPU needed): parses the blob for `game` exactly like
+ * spb_load_weights and reports SPB_OK or SPB_ERR_WEIGHTS with the reason in err[0..err_cap).
+ */
+int32_t spb_check_weights(int32_t game, const void* safetensors_blob, size_t num_bytes, char* err, size_t err_cap);
 
 /* ---- trees (ref: Tree::default mcts.rs:67, Tree::with_root_state mcts.rs:86) ---- */
 
@@ -209,15 +219,15 @@ int32_t spb_game_encode(spb_engine* e, const spb_state* states, uint32_t n, floa
 #define SPB_MOVE_GREEDY_LAST_MAX 0  /* ref: main.rs:108-112 (arg-max visit count, last max wins) */
 #define SPB_MOVE_TEMPERATURE     1  /* ref: learner_concurrent.rs:189-194 (sample ∝ N^temperature), counter-based RNG */
 
-/* One finished-or-not position record of a trajectory (compact 48-byte form). */
+/* One position record of a finished trajectory (compact form of `Payload`, learner_concurrent.rs:13-18). */
 typedef struct spb_position {
   uint64_t stones[2];            /* position the search was run from (root state) */
-  uint32_t visit_counts[7];      /* root child visit counts scattered BY ACTION (Connect4: column) */
+  uint32_t visit_counts[SPB_MAX_ACTIONS]; /* root child visit counts scattered BY ACTION (policy target before normalising) */
   uint8_t  current_player;
   uint8_t  ply;                  /* index of this position inside its game */
   int8_t   outcome;              /* value target for this position: +1 / 0 / -1 (learner_concurrent.rs:214-226) */
   uint8_t  reserved;
-} spb_position;                  /* 48 bytes */
+} spb_position;                  /* 56 bytes */
 
 /*
  * One self-play ply for every live slot, entirely on the device: pick a child of

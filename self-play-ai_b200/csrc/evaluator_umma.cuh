@@ -1,0 +1,19 @@
+// evaluator_umma.cuh — interface of the tcgen05 evaluator kernel (evaluator_umma.cu).
+#pragma once
+#include <cstdint>
+#include <vector>
+
+#include "evaluator.cuh"
+
+namespace spb {
+namespace umma {
+
+// Packs the folded net into the device image the tcgen05 kernel streams with TMA bulk copies.
+void pack_weights(const HostNet& net, std::vector<uint8_t>* out);
+
+cudaError_t launch(const Evaluator::DevNet& net, int game, const PState* states, const uint32_t* list,
+                   const uint32_t* count_dev, uint32_t max_n, float* out, int stride, float* logits_out,
+                   cudaStream_t stream);
+
+}  // namespace umma
+}  // namespace spb

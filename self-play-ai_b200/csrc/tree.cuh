@@ -1,0 +1,203 @@
+// tree.cuh — structure-of-arrays MCTS node pools in HBM and the warp-per-tree primitives.
+//
+// Replaces src/mcts.rs of the reference: Node (mcts.rs:20-30), Tree (:32-39), get_ucb (:91-100),
+// select (:102-114), expand (:116-143), backprop (:145-159), use_subtree (:161-192).
+//
+// Layout (per engine):
+//   rec[b][g*cap + id]   16 B  {visit_count u32, value_sum f32, prior f32, info u32}
+//                              info = first_child[0,24) | n_children[24,28) | status[28,30)
+//                              A parent's children are contiguous and in get_valid_actions order
+//                              (mcts.rs:121-122), so 7 children = 112 contiguous bytes read as
+//                              one LDG.128 per lane.
+//   par[b][g*cap + id]    4 B  parent_id[0,24) | action_taken[24,32)   (root: parent 0xFFFFFF)
+//   b = buf[g] selects one of two arenas; use_subtree compacts from one into the other.
+//   root_state[g]        16 B  packed position of arena[0]; node states are NOT stored — a warp
+//                              replays the moves while it descends (a few bitboard ops per level).
+#pragma once
+#include "games.cuh"
+
+namespace spb {
+
+struct __align__(16) NodeRec {
+  uint32_t N;
+  float W;
+  float P;
+  uint32_t info;
+};
+static_assert(sizeof(NodeRec) == 16, "NodeRec must be 16 bytes");
+
+constexpr uint32_t INFO_FC_MASK = 0xFFFFFFu;
+constexpr int INFO_NC_SHIFT = 24, INFO_STATUS_SHIFT = 28;
+constexpr uint32_t PAR_NONE = 0xFFFFFFu;
+constexpr uint32_t MAX_CAP = 1u << 24;
+
+__host__ __device__ __forceinline__ uint32_t info_fc(uint32_t info) { return info & INFO_FC_MASK; }
+__host__ __device__ __forceinline__ uint32_t info_nc(uint32_t info) { return (info >> INFO_NC_SHIFT) & 15u; }
+__host__ __device__ __forceinline__ uint32_t info_status(uint32_t info) { return (info >> INFO_STATUS_SHIFT) & 3u; }
+__host__ __device__ __forceinline__ uint32_t make_info(uint32_t fc, uint32_t nc, uint32_t status) {
+  return (fc & INFO_FC_MASK) | (nc << INFO_NC_SHIFT) | (status << INFO_STATUS_SHIFT);
+}
+
+enum CounterIdx { CTR_SIMS = 0, CTR_EVALS, CTR_TERMINAL, CTR_PATHSUM, CTR_CHILDREN, CTR_COUNT };
+enum ErrorBits : uint32_t { ERRBIT_POOL = 1u, ERRBIT_NAN = 2u };
+
+// leaf_info[slot]: depth[0,8) | pending-eval flag (bit 8)
+constexpr uint32_t LEAF_PENDING = 1u << 8;
+
+struct Trees {
+  NodeRec* rec[2];
+  uint32_t* par[2];
+  PState* root_state;
+  uint32_t* n_nodes;
+  uint8_t* buf;
+  uint8_t* live;
+  uint32_t cap;
+  uint32_t G;
+  uint32_t K;            // leaves per tree per step
+  float c;
+  // per leaf slot (g*K + k)
+  uint32_t* path;        // [G*K][MAX_DEPTH]
+  uint32_t* leaf_info;   // [G*K]
+  PState* leaf_state;    // [G*K]  evaluator input
+  uint32_t* eval_list;   // [G*K]  compacted leaf slots that need the evaluator
+  uint32_t* eval_count;  // [1]
+  float* eval_out;       // [G*K][EVAL_STRIDE]  probs (softmax, unmasked) + value
+  unsigned long long* counters;  // [CTR_COUNT]
+  uint32_t* error;       // [1]
+};
+
+// get_ucb, mcts.rs:91-100 — every operation individually rounded (no FMA contraction), evaluated in
+// the reference's order: q + ((c * prior) * sqrt(N_parent)) / (1 + N_child).
+__device__ __forceinline__ float puct_score(float c, uint32_t n_parent, uint32_t n_child, float w_child, float prior) {
+  float q = 0.0f;                                              // :95 unvisited child -> q = 0.0
+  if (n_child != 0)
+    q = __fdiv_rn(__fadd_rn(__fdiv_rn(-w_child, (float)n_child), 1.0f), 2.0f);   // :97
+  float u = __fmul_rn(c, prior);
+  u = __fmul_rn(u, __fsqrt_rn((float)n_parent));
+  u = __fdiv_rn(u, __fadd_rn(1.0f, (float)n_child));
+  return __fadd_rn(q, u);
+}
+
+// select, mcts.rs:102-114: arg-max over the children with Iterator::max_by semantics — among equal
+// maxima the LAST child wins.  Lanes >= nc carry (-inf, -1).  Returns the winning child index.
+__device__ __forceinline__ int warp_argmax_last(float score, int idx) {
+#pragma unroll
+  for (int off = 8; off >= 1; off >>= 1) {
+    float os = __shfl_xor_sync(0xffffffffu, score, off);
+    int oi = __shfl_xor_sync(0xffffffffu, idx, off);
+    if (os > score || (os == score && oi > idx)) { score = os; idx = oi; }
+  }
+  return idx;   // lanes 0..15 agree; callers broadcast from lane 0
+}
+
+// Path of one simulation, distributed over the warp: lane d holds depth d (set 0) and depth d+32 (set 1).
+struct WarpPath {
+  uint32_t node[2];
+  uint32_t N[2];
+  float W[2];
+};
+
+// Descend from the root to a leaf (mcts.rs:237-241), replaying the moves on the bitboards.
+// All lanes return the same (leaf, depth, st, leaf_info).
+template <class G>
+__device__ __forceinline__ void descend(const NodeRec* rec, const PState& root, float c, int lane,
+                                        WarpPath& path, uint32_t& leaf, int& depth, PState& st, uint32_t& leaf_info,
+                                        uint32_t* err) {
+  NodeRec r0 = rec[0];
+  uint32_t node = 0, Np = r0.N, info = r0.info;
+  st = root;
+  depth = 0;
+  if (lane == 0) { path.node[0] = 0; path.N[0] = r0.N; path.W[0] = r0.W; }
+  while (info_nc(info) != 0) {
+    const int nc = (int)info_nc(info);
+    const uint32_t fc = info_fc(info);
+    NodeRec ch;
+    ch.N = 0; ch.W = 0.0f; ch.P = 0.0f; ch.info = 0;
+    float score = -INFINITY;
+    int idx = -1;
+    if (lane < nc) {
+      ch = rec[fc + lane];                                   // 16-B vector load, children contiguous
+      score = puct_score(c, Np, ch.N, ch.W, ch.P);
+      idx = lane;
+      if (score != score) atomicOr(err, ERRBIT_NAN);         // the reference would panic (partial_cmp().unwrap())
+    }
+    int best = warp_argmax_last(score, idx);
+    best = __shfl_sync(0xffffffffu, best, 0);
+    uint32_t bN = __shfl_sync(0xffffffffu, ch.N, best);
+    float bW = __shfl_sync(0xffffffffu, ch.W, best);
+    uint32_t binfo = __shfl_sync(0xffffffffu, ch.info, best);
+    uint32_t legal = G::valid_mask(st);
+    int action = nth_set_bit(legal, best);
+    st = G::place(st, action, info_status(binfo));
+    node = fc + (uint32_t)best;
+    ++depth;
+    if (lane == (depth & 31)) {
+      int s = depth >> 5;
+      path.node[s] = node; path.N[s] = bN; path.W[s] = bW;
+    }
+    Np = bN;
+    info = binfo;
+  }
+  leaf = node;
+  leaf_info = info;
+}
+
+// backprop, mcts.rs:145-159, with the path held in registers: lane d updates the node at depth d.
+// The leaf gets +v, its parent -v, ... (sign flips at every level).
+__device__ __forceinline__ void backup_regs(NodeRec* rec, const WarpPath& path, int depth, float v, int lane) {
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    int d = lane + 32 * s;
+    if (d <= depth) {
+      float sv = ((depth - d) & 1) ? -v : v;
+      uint2 nw;
+      nw.x = path.N[s] + 1u;
+      nw.y = __float_as_uint(__fadd_rn(path.W[s], sv));
+      *reinterpret_cast<uint2*>(&rec[path.node[s]]) = nw;   // {N, W} are the first 8 bytes of the record
+    }
+  }
+}
+
+// backprop with the path in global scratch (the evaluator kernel ran in between).
+__device__ __forceinline__ void backup_mem(NodeRec* rec, const uint32_t* path, int depth, float v, int lane) {
+  for (int d = lane; d <= depth; d += 32) {
+    uint32_t node = path[d];
+    uint2 nw = *reinterpret_cast<const uint2*>(&rec[node]);
+    float sv = ((depth - d) & 1) ? -v : v;
+    nw.x += 1u;
+    nw.y = __float_as_uint(__fadd_rn(__uint_as_float(nw.y), sv));
+    *reinterpret_cast<uint2*>(&rec[node]) = nw;
+  }
+}
+
+// expand, mcts.rs:116-143: append one child per legal action (ascending action order), ids contiguous
+// [n_nodes, n_nodes+nc).  probs = evaluator output BEFORE masking; mask_invalid_actions is applied here
+// (model/mod.rs:86-93).  Returns false on pool overflow.
+template <class G>
+__device__ __forceinline__ bool expand(NodeRec* rec, uint32_t* par, uint32_t cap, uint32_t& n_nodes, uint32_t leaf,
+                                       const PState& st, const float* probs, int lane) {
+  const uint32_t legal = G::valid_mask(st);
+  const int nc = __popc(legal);
+  const uint32_t first = n_nodes;
+  if (first + (uint32_t)nc > cap) return false;
+  float priors[G::A];
+  mask_renorm<G>(legal, probs, priors);
+  if (lane < nc) {
+    int a = nth_set_bit(legal, lane);
+    PState child;
+    G::next_state(st, a, &child);                            // :129 (cannot fail: a is legal)
+    float p = 0.0f;
+#pragma unroll
+    for (int k = 0; k < G::A; ++k) if (k == a) p = priors[k];   // :128 policy.get_prob(&action)
+    NodeRec r;
+    r.N = 0; r.W = 0.0f; r.P = p;
+    r.info = make_info(0, 0, ps_status(child));
+    rec[first + lane] = r;
+    par[first + lane] = leaf | ((uint32_t)a << 24);
+  }
+  if (lane == 0) rec[leaf].info = make_info(first, (uint32_t)nc, SPB_STATUS_ONGOING);
+  n_nodes = first + (uint32_t)nc;
+  return true;
+}
+
+}  // namespace spb

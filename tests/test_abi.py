@@ -1,0 +1,90 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads, exports every symbol that
+include/selfplay_b200.h declares, and its host-only logic behaves (no compute calls without a GPU)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import selfplay_b200 as S
+import torch_net
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = open(os.path.join(ROOT, "include", "selfplay_b200.h")).read()
+
+
+def declared_symbols():
+    return sorted(set(re.findall(r"\b(spb_[a-z_0-9]+)\s*\(", HEADER)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = S.load_library()
+    names = declared_symbols()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(L, n), "missing export: " + n
+    assert set(names) == set(S.engine.ABI), set(names) ^ set(S.engine.ABI)
+    assert L.spb_abi_version() == 1 == int(re.search(r"#define SPB_ABI_VERSION (\d+)", HEADER).group(1))
+
+
+def test_struct_layouts_match_header():
+    assert C.sizeof(S.State) == 24 and C.sizeof(S.Position) == 56
+    assert C.sizeof(S.Config) == 16 * 4 and C.sizeof(S.Counters) == 12 * 8
+    cfg = S.Config()
+    assert S.load_library().spb_default_config(C.byref(cfg)) == 0
+    # defaults mirror Args::default (mcts.rs:46-59)
+    assert (cfg.game, cfg.num_games, cfg.c, cfg.leaves_per_tree, cfg.evaluator) == (S.GAME_C4, 100, 2.0, 1, S.EVAL_NET)
+
+
+def test_create_fails_loudly_without_a_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(S.EngineError) as ei:
+        S.Engine(num_games=4, evaluator=S.EVAL_DET)
+    assert ei.value.code == -2 and "no CPU fallback" in str(ei.value)
+
+
+def test_create_rejects_bad_config():
+    L = S.load_library()
+    cfg = S.Config()
+    L.spb_default_config(C.byref(cfg))
+    h = C.c_void_p()
+    for field, val in [("abi_version", 99), ("game", 7), ("num_games", 0), ("leaves_per_tree", 0), ("evaluator", 9)]:
+        bad = S.Config.from_buffer_copy(cfg)
+        setattr(bad, field, val)
+        assert L.spb_create(C.byref(bad), C.byref(h)) == -1, field
+        assert L.spb_last_error(None)
+    assert L.spb_create(None, C.byref(h)) == -1
+    assert L.spb_destroy(None) == -1 and L.spb_search(None, 1) == -1
+
+
+@pytest.mark.parametrize("game", [S.GAME_TTT, S.GAME_C4])
+def test_check_weights_accepts_both_naming_schemes(game):
+    net = torch_net.make_net(game, seed=3)
+    for blob in (torch_net.to_safetensors_tch(net), torch_net.to_safetensors_explicit(net),
+                 torch_net.to_safetensors_tch(net, shuffle_seed=5),
+                 torch_net.to_safetensors_tch(net, bn_order=("running_mean", "running_var", "weight", "bias"))):
+        rc, msg = S.check_weights(game, blob)
+        assert rc == 0, msg
+
+
+def test_check_weights_rejects_garbage():
+    net = torch_net.make_net(S.GAME_C4, seed=3)
+    blob = torch_net.to_safetensors_tch(net)
+    assert S.check_weights(S.GAME_C4, b"\x00" * 4)[0] == -5
+    assert S.check_weights(S.GAME_C4, blob[:1000])[0] == -5
+    rc, msg = S.check_weights(S.GAME_TTT, blob)          # Connect4 checkpoint into the tic-tac-toe net
+    assert rc == -5 and "shape" in msg
+    import struct
+    hdr_len = struct.unpack("<Q", blob[:8])[0]
+    rc, msg = S.check_weights(S.GAME_C4, blob[:8] + b"{" + b"x" * (hdr_len - 1) + blob[8 + hdr_len:])
+    assert rc == -5
+
+
+def test_tch_names_look_like_a_varstore():
+    names = [k for k in __import__("json").loads(torch_net.to_safetensors_tch(torch_net.make_net(1))[8:].split(b"}}")[0] + b"}}")]
+    assert "bias" in names and "weight" in names and "running_mean" in names
+    assert any(re.fullmatch(r"weight__\d+", n) for n in names)
+    assert len(names) == 70     # 70 VarStore tensors
