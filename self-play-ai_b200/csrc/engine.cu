@@ -230,9 +230,10 @@ __device__ void reroot(const Trees& T, uint32_t g, uint32_t new_root, int lane) 
   }
   __syncwarp();
   uint32_t next = 1;
-  for (uint32_t lo = 0; lo < next; lo += 32) {
+  for (uint32_t lo = 0; lo < next;) {
+    const uint32_t hi = min(next, lo + 32u);                   // nodes [lo, hi) are already in the new arena
     const uint32_t i = lo + lane;
-    const bool active = i < next;
+    const bool active = i < hi;
     uint32_t info = active ? nrec[i].info : 0u;
     const uint32_t nc = info_nc(info), ofc = info_fc(info);
     uint32_t incl = nc;
@@ -251,6 +252,7 @@ __device__ void reroot(const Trees& T, uint32_t g, uint32_t new_root, int lane) 
       nrec[i].info = make_info(nc ? nfc : 0u, nc, info_status(info));
     }
     next += total;
+    lo = hi;
     __syncwarp();
   }
   if (lane == 0) {

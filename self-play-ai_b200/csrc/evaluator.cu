@@ -88,9 +88,7 @@ __global__ void __launch_bounds__(256) k_eval_simt(Evaluator::DevNet net, const 
                       [&](int oc, int p, float v) { ha[oc * P + p] = round_bf16(fmaxf(v, 0.0f)); });
       __syncthreads();
       conv3x3_simt<G>(ha, NET_HIDDEN, net.w_simt[2 + 2 * b], net.bias[2 + 2 * b], NET_HIDDEN,
-                      [&](int oc, int p, float v) { ha[oc * P + p] = v; });   // staged: xa is still being read
-      __syncthreads();
-      for (int idx = threadIdx.x; idx < NET_HIDDEN * P; idx += blockDim.x) xa[idx] = round_bf16(fmaxf(ha[idx] + xa[idx], 0.0f));
+                      [&](int oc, int p, float v) { xa[oc * P + p] = round_bf16(fmaxf(v + xa[oc * P + p], 0.0f)); });   // (x + f(x)).relu()
       __syncthreads();
     }
     conv3x3_simt<G>(xa, NET_HIDDEN, net.w_simt[9], net.bias[9], NET_POLICY_CH,
