@@ -254,6 +254,13 @@ int32_t spb_reset_counters(spb_engine* e);
 int32_t spb_last_search_timing(spb_engine* e, float* search_ms, float* evaluator_ms,
                                uint32_t* evaluator_launches);
 int32_t spb_synchronize(spb_engine* e);
+/*
+ * Re-runs the evaluator kernel `iters` times on the work list of the most recent lock-step search (the leaves of
+ * its last simulation step, still resident in HBM) and reports the average launch duration, measured with CUDA
+ * events on the engine's stream, the number of positions per launch and the FLOPs per position (2*MAC).
+ * Used by bench.py for the tensor roofline of the dominant kernel.
+ */
+int32_t spb_time_evaluator(spb_engine* e, uint32_t iters, float* avg_ms, uint32_t* n_positions, double* flops_per_position);
 
 #ifdef __cplusplus
 }

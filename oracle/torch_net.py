@@ -134,3 +134,38 @@ def forward_probs(net, enc):
         x = torch.from_numpy(np.ascontiguousarray(enc, dtype=np.float32))
         p, v = net(x)
         return torch.softmax(p, -1).numpy(), v.reshape(-1).numpy(), p.numpy()
+
+
+def load_tch_safetensors(blob: bytes, game: int):
+    """Builds the torch net from a tch-style checkpoint (names de-duplicated with "__{n}", creation order)."""
+    hlen = struct.unpack("<Q", blob[:8])[0]
+    header = json.loads(blob[8:8 + hlen])
+    data = blob[8 + hlen:]
+    items = []
+    for name, meta in header.items():
+        if name == "__metadata__":
+            continue
+        base, _, idx = name.partition("__")
+        arr = np.frombuffer(data[meta["data_offsets"][0]:meta["data_offsets"][1]], dtype=np.float32).reshape(meta["shape"])
+        items.append((int(idx) if idx else -1, base, arr))
+    items.sort(key=lambda t: t[0])
+    rows, cols, actions = (6, 7, 7) if game == 1 else (3, 3, 9)
+    net = Net(rows, cols, actions).eval()
+    it = iter(items)
+    def take(n):
+        got = {}
+        for _ in range(n):
+            _, base, arr = next(it)
+            got[base] = torch.from_numpy(arr.copy())
+        return got
+    with torch.no_grad():
+        def fill_conv(c):
+            g = take(2); c.weight.copy_(g["weight"]); c.bias.copy_(g["bias"])
+        def fill_bn(b):
+            g = take(4); b.weight.copy_(g["weight"]); b.bias.copy_(g["bias"]); b.running_mean.copy_(g["running_mean"]); b.running_var.copy_(g["running_var"])
+        pairs = net.conv_bn_pairs()
+        for c, b in pairs[:-2]:
+            fill_conv(c); fill_bn(b)
+        fill_conv(net.pconv); fill_bn(net.pbn); fill_conv(net.pfc)
+        fill_conv(net.vconv); fill_bn(net.vbn); fill_conv(net.vfc)
+    return net

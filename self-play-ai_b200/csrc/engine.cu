@@ -482,6 +482,7 @@ struct spb_engine {
   uint64_t launches = 0;
   float last_search_ms = 0.f, last_eval_ms = 0.f;
   uint32_t last_eval_launches = 0;
+  int last_eval_parity = -1;   // parity of the work list the last evaluator launch of spb_search consumed
   // CUDA graph of one split-pipeline step pair (parity 0 and 1)
   cudaGraphExec_t step_graph = nullptr;
   int A = 0, max_depth = 0, eval_stride = 0, max_ply = 0;
@@ -553,7 +554,7 @@ int32_t spb_engine::init() {
   if ((rc = dalloc(&T.leaf_info, slots))) return rc;
   if ((rc = dalloc(&T.leaf_state, slots))) return rc;
   if ((rc = dalloc(&T.eval_list, slots))) return rc;
-  if ((rc = dalloc(&T.eval_count, 2))) return rc;
+  if ((rc = dalloc(&T.eval_count, 4))) return rc;   // [0],[1] ping-pong, [2] snapshot for spb_time_evaluator
   if ((rc = dalloc(&T.eval_out, slots * eval_stride))) return rc;
   if ((rc = dalloc(&T.counters, (size_t)CTR_COUNT))) return rc;
   if ((rc = dalloc(&T.error, 1))) return rc;
@@ -577,7 +578,7 @@ int32_t spb_engine::init() {
   SPB_CUDA(cudaMemsetAsync(T.buf, 0, G, stream));
   SPB_CUDA(cudaMemsetAsync(T.n_nodes, 0, G * 4, stream));
   SPB_CUDA(cudaMemsetAsync(T.leaf_info, 0, slots * 4, stream));
-  SPB_CUDA(cudaMemsetAsync(T.eval_count, 0, 8, stream));
+  SPB_CUDA(cudaMemsetAsync(T.eval_count, 0, 16, stream));
   SPB_CUDA(cudaMemsetAsync(T.eval_out, 0, slots * eval_stride * 4, stream));
   SPB_CUDA(cudaMemsetAsync(T.counters, 0, CTR_COUNT * 8, stream));
   SPB_CUDA(cudaMemsetAsync(T.error, 0, 4, stream));
@@ -684,6 +685,10 @@ int32_t spb_engine::search_t(uint32_t num_searches) {
       SPB_CHECK_LAUNCH();
       ++last_eval_launches;
       const int last = (j == num_searches - 1);
+      if (last) {   // keep the size of the last work list: the final tree step clears the ping-pong counter
+        SPB_CUDA(cudaMemcpyAsync(&T.eval_count[2], &T.eval_count[j & 1u], 4, cudaMemcpyDeviceToDevice, stream));
+        last_eval_parity = 2;
+      }
       k_tree_step<G><<<blocks, THREADS, 0, stream>>>(T, 1, last ? 0 : 1, j + 1);
       SPB_CHECK_LAUNCH();
       ++launches;
@@ -1248,6 +1253,34 @@ int32_t spb_last_search_timing(spb_engine* e, float* search_ms, float* evaluator
   if (search_ms) *search_ms = e->last_search_ms;
   if (evaluator_ms) *evaluator_ms = e->last_eval_ms;
   if (evaluator_launches) *evaluator_launches = e->last_eval_launches;
+  return SPB_OK;
+}
+
+int32_t spb_time_evaluator(spb_engine* e, uint32_t iters, float* avg_ms, uint32_t* n_positions, double* flops_per_position) {
+  ENGINE_GUARD(e);
+  ARG_CHECK(e, iters > 0 && avg_ms, "bad argument");
+  if (e->cfg.evaluator != SPB_EVAL_NET || !e->evaluator.loaded()) { e->set_error("needs the network evaluator with weights loaded"); return SPB_ERR_STATE; }
+  if (e->last_eval_parity < 0) { e->set_error("run spb_search first"); return SPB_ERR_STATE; }
+  const uint32_t slots = e->T.G * e->T.K;
+  const uint32_t* cnt = &e->T.eval_count[2];
+  const bool simt = (e->cfg.flags & SPB_FLAG_EVAL_SIMT) != 0;
+  cudaError_t ce = cudaSuccess;
+  for (int w = 0; w < 2 && ce == cudaSuccess; ++w)    // warm-up
+    ce = e->evaluator.launch(e->T.leaf_state, e->T.eval_list, cnt, slots, e->T.eval_out, e->eval_stride, nullptr, simt, e->stream);
+  if (ce == cudaSuccess) ce = cudaEventRecord(e->ev0, e->stream);
+  for (uint32_t i = 0; i < iters && ce == cudaSuccess; ++i)
+    ce = e->evaluator.launch(e->T.leaf_state, e->T.eval_list, cnt, slots, e->T.eval_out, e->eval_stride, nullptr, simt, e->stream);
+  if (ce == cudaSuccess) ce = cudaEventRecord(e->ev1, e->stream);
+  uint32_t n = 0;
+  if (ce == cudaSuccess) ce = cudaMemcpyAsync(&n, cnt, 4, cudaMemcpyDeviceToHost, e->stream);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+  float ms = 0.f;
+  if (ce == cudaSuccess) ce = cudaEventElapsedTime(&ms, e->ev0, e->ev1);
+  if (ce != cudaSuccess) { e->set_error(std::string("spb_time_evaluator: ") + cudaGetErrorString(ce)); return SPB_ERR_CUDA; }
+  e->launches += iters + 2;
+  *avg_ms = ms / (float)iters;
+  if (n_positions) *n_positions = n;
+  if (flops_per_position) *flops_per_position = e->evaluator.flops_per_position();
   return SPB_OK;
 }
 

@@ -98,6 +98,7 @@ ABI = {
     "spb_reset_counters": (C.c_int32, [_vp]),
     "spb_last_search_timing": (C.c_int32, [_vp, _f32p, _f32p, _u32p]),
     "spb_synchronize": (C.c_int32, [_vp]),
+    "spb_time_evaluator": (C.c_int32, [_vp, C.c_uint32, _f32p, _u32p, C.POINTER(C.c_double)]),
 }
 
 
@@ -317,6 +318,12 @@ class Engine:
         s, ev, n = C.c_float(), C.c_float(), C.c_uint32()
         self._chk(self._L.spb_last_search_timing(self._h, C.byref(s), C.byref(ev), C.byref(n)))
         return s.value, ev.value, n.value
+
+    def time_evaluator(self, iters=20):
+        """-> (avg launch ms, positions per launch, FLOPs per position) of the evaluator kernel on the last work list."""
+        ms, n, fl = C.c_float(), C.c_uint32(), C.c_double()
+        self._chk(self._L.spb_time_evaluator(self._h, iters, C.byref(ms), C.byref(n), C.byref(fl)))
+        return ms.value, n.value, fl.value
 
     def synchronize(self):
         self._chk(self._L.spb_synchronize(self._h))

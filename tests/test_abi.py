@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 import selfplay_b200 as S
-import torch_net
+from oracle import torch_net
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HEADER = open(os.path.join(ROOT, "include", "selfplay_b200.h")).read()

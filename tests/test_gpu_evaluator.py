@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 import selfplay_b200 as S
-import torch_net
+from oracle import torch_net
 from helpers import random_states, synthetic_roots
 from oracle import pyoracle as O
 

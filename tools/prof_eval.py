@@ -3,7 +3,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 import selfplay_b200 as S
 from selfplay_b200.synth import synthetic_roots_device
-import torch_net
+from oracle import torch_net
 G = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 sims = int(sys.argv[2]) if len(sys.argv) > 2 else 40
 net = torch_net.make_net(1, seed=0, randomize_bn=False)

@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(
 import numpy as np
 import selfplay_b200 as S
 from selfplay_b200.synth import synthetic_roots_device
-import torch_net
+from oracle import torch_net
 
 G = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 sims = int(sys.argv[2]) if len(sys.argv) > 2 else 800
