@@ -19,12 +19,12 @@
 //   D          fp32 accumulators in TMEM, one 64-column block per tile (4 x 64 = 256 columns).
 //   MMA        tcgen05.mma.cta_group::1.kind::f16, M=128, N=64 (48 for the fused policy+value head conv),
 //              K=16; 9 taps x 4 k-steps accumulate one tile of one layer.
-//   epilogue   4 warps: tcgen05.ld -> +bias (+skip) -> ReLU -> bf16 -> st.shared into the other activation
+//   epilogue   8 warps (two per TMEM lane quadrant, 32 channels each): tcgen05.ld -> +bias (+skip) -> ReLU -> bf16 -> st.shared into the other activation
 //              buffer (pad rows forced to zero), which is the next layer's A operand.  Head layer: the two
 //              Linear layers, softmax and tanh are computed from the accumulators.
 //
 // Warp roles: warp 0 = weight producer (one lane), warp 1 = TMEM allocator + MMA issuer (one lane),
-// warps 2..5 = epilogue (TMEM lane quadrant = warp & 3).  Hand-offs are mbarriers only.
+// warps 2..9 = epilogue (TMEM lane quadrant = warp & 3, channel half = (warp-2)/4).  Hand-offs are mbarriers only.
 #include <cuda_bf16.h>
 
 #include <cstring>
@@ -166,7 +166,14 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) { asm volatile("tcgen0
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+// One elected lane of a fully converged warp (cute::elect_one_sync): lets the compiler keep tcgen05 operands in
+// uniform registers instead of emitting a per-lane waterfall loop around every instruction.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred P1;\nelect.sync _|P1, 0xffffffff;\nselp.u32 %0, 1, 0, P1;\n}" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -198,13 +205,23 @@ __device__ __forceinline__ float bf_hi(uint32_t u) { return __uint_as_float(u & 
 // kk * 2Q (two K chunks further), B = slot base + tap * slot stride + kk * 2N; high words are constants.
 template <int W8, int Q, int KSTEPS, int N>
 __device__ __forceinline__ void issue_tile(bool issuer, uint32_t a_lo_tile, uint32_t b_lo_base, uint32_t slot_stride16,
-                                           uint32_t d_tmem, bool first_tile, bool last_tile, uint32_t w_par, uint32_t bar_base) {
+                                           uint32_t d_tmem, bool first_tile, bool last_tile, uint32_t w_par, uint32_t bar_base,
+                                           unsigned long long& prof_wfull) {
   constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);          // SBO = 128 B, descriptor version 1
   constexpr uint32_t IDESC = make_idesc(N);
   (void)slot_stride16;
 #pragma unroll
   for (int tap = 0; tap < 9; ++tap) {
-    if (first_tile) { mbar_wait(bar_base + (uint32_t)tap * 8u, w_par); tc_fence_after(); }      // w_full[tap]
+    if (first_tile) {                                                                            // w_full[tap]
+#ifdef SPB_PROFILE
+      const unsigned long long t0 = clock64();
+#endif
+      mbar_wait(bar_base + (uint32_t)tap * 8u, w_par);
+#ifdef SPB_PROFILE
+      prof_wfull += clock64() - t0;
+#endif
+      tc_fence_after();
+    }
     const int shift = (tap / 3 - 1) * W8 + (tap % 3 - 1);
     if (issuer) {
 #pragma unroll
@@ -233,15 +250,33 @@ struct Smem {
   static constexpr int OFF_W = 2 * ACT_BYTES;                      // 9 x 8 KB weight ring
   static constexpr int OFF_BIAS = OFF_W + N_SLOTS * SLOT_BYTES;    // 10 x 64 f32
   static constexpr int OFF_LOGITS = OFF_BIAS + N_LAYERS * 64 * 4;  // [NB][16] f32 (policy partial sums, value at [15])
-  static constexpr int OFF_STATES = OFF_LOGITS + Ge::NB * 16 * 4;  // [NB] PState
-  static constexpr int OFF_SLOTS = OFF_STATES + Ge::NB * 16;       // [NB] u32
-  static constexpr int OFF_BARS = (OFF_SLOTS + Ge::NB * 4 + 15) & ~15;
-  // barriers: w_full[9], w_empty[9], acc_full[4], act_ready[4]
-  static constexpr int OFF_TMEM = OFF_BARS + (2 * N_SLOTS + 2 * Ge::NT) * 8;
+  static constexpr int OFF_PART = OFF_LOGITS + Ge::NB * 16 * 4;    // [NB][ROWS][16] f32 row partials of the Linear layers
+  static constexpr int OFF_STATES = OFF_PART + Ge::NB * G::ROWS * 16 * 4;   // [2][NB] PState
+  static constexpr int OFF_SLOTS = OFF_STATES + 2 * Ge::NB * 16;   // [2][NB] u32 (states/slots ping-pong per batch)
+  static constexpr int OFF_BARS = (OFF_SLOTS + 2 * Ge::NB * 4 + 15) & ~15;
+  // barriers: w_full[9], w_empty[9], acc_full[4], act_ready[4], stage_ready[4], acc_full of odd batches [4]
+  static constexpr int OFF_TMEM = OFF_BARS + (2 * N_SLOTS + 4 * Ge::NT) * 8;
   static constexpr int TOTAL = OFF_TMEM + 16;
 };
 
-constexpr int THREADS = 192;
+static_assert(Smem<Connect4>::TOTAL <= 232448 && Smem<TicTacToe>::TOTAL <= 232448, "shared memory plan exceeds 227 KB");
+constexpr int THREADS = 320;     // producer warp, MMA warp, 8 epilogue warps
+
+#ifdef SPB_PROFILE
+// debug build only (make PROFILE=1): per-CTA cycle attribution
+__device__ unsigned long long g_eval_prof[160][8];
+__device__ unsigned long long g_eval_prof_layer[160][24];   // [cta][0..9] act waits per layer, [10..19] weight waits per layer
+__device__ int g_eval_debug = 0;   // bit0: epilogue skips tcgen05.ld, bit1: skips st.shared, bit2: skips skip-loads, bit3: no per-tap commits
+#define DBG(bit) (g_eval_debug & (1 << (bit)))
+#define PROF_DECL unsigned long long prof_t0 = 0, prof_acc0 = 0, prof_acc1 = 0, prof_acc2 = 0;
+#define PROF_BEGIN() (prof_t0 = clock64())
+#define PROF_END(acc) ((acc) += clock64() - prof_t0)
+#else
+#define DBG(bit) 0
+#define PROF_DECL
+#define PROF_BEGIN() ((void)0)
+#define PROF_END(acc) ((void)0)
+#endif
 
 template <class G>
 __global__ void __launch_bounds__(THREADS, 1)
@@ -262,8 +297,13 @@ k_eval_umma(const uint8_t* __restrict__ image, const PState* __restrict__ states
   const uint32_t bar_base = s_base + Sm::OFF_BARS;
   auto bar_w_full = [&](int s) { return bar_base + (uint32_t)s * 8u; };
   auto bar_w_empty = [&](int s) { return bar_base + (uint32_t)(N_SLOTS + s) * 8u; };
-  auto bar_acc_full = [&](int t) { return bar_base + (uint32_t)(2 * N_SLOTS + t) * 8u; };
+  // acc_full is per accumulator set (batch parity): the MMA warp may finish the next batch's stem tile before the
+  // epilogue has consumed this batch's head tile, and an mbarrier must never run two phases ahead of a waiter.
+  auto bar_acc_full = [&](uint32_t set, int t) { return bar_base + (uint32_t)(2 * N_SLOTS + (set ? 3 * Ge::NT : 0) + t) * 8u; };
   auto bar_act_ready = [&](int t) { return bar_base + (uint32_t)(2 * N_SLOTS + Ge::NT + t) * 8u; };
+  // separate barrier for the staged input of a batch: it may complete while act_ready's previous phase is still
+  // being consumed by the MMA warp (an mbarrier must never run two phases ahead of a waiter)
+  auto bar_stage_ready = [&](int t) { return bar_base + (uint32_t)(2 * N_SLOTS + 2 * Ge::NT + t) * 8u; };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + Sm::OFF_TMEM);
 
   // ---- one-time setup -----------------------------------------------------------------------------
@@ -277,10 +317,10 @@ k_eval_umma(const uint8_t* __restrict__ image, const PState* __restrict__ states
   }
   if (tid == 0) {
     for (int s = 0; s < N_SLOTS; ++s) { mbar_init(bar_w_full(s), 1); mbar_init(bar_w_empty(s), 1); }
-    for (int t = 0; t < Ge::NT; ++t) { mbar_init(bar_acc_full(t), 1); mbar_init(bar_act_ready(t), 128); }
+    for (int t = 0; t < Ge::NT; ++t) { mbar_init(bar_acc_full(0, t), 1); mbar_init(bar_acc_full(1, t), 1); mbar_init(bar_act_ready(t), 256); mbar_init(bar_stage_ready(t), 256); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 256);
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -298,7 +338,7 @@ k_eval_umma(const uint8_t* __restrict__ image, const PState* __restrict__ states
           const uint32_t bytes = (uint32_t)layer_tap_bytes(l);
           const uint8_t* src = image + layer_offset(l);
           for (int s = 0; s < N_SLOTS; ++s) {
-            if (use > 0) mbar_wait_sleep(bar_w_empty(s), (use - 1) & 1u);
+            if (use > 0) mbar_wait(bar_w_empty(s), (use - 1) & 1u);
             mbar_expect_tx(bar_w_full(s), bytes);
             bulk_g2s(s_base + Sm::OFF_W + (uint32_t)s * SLOT_BYTES, src + (size_t)s * bytes, bytes, bar_w_full(s));
           }
@@ -311,195 +351,270 @@ k_eval_umma(const uint8_t* __restrict__ image, const PState* __restrict__ states
     // The whole warp runs the (warp-uniform) control flow so that descriptors stay in uniform registers;
     // one fixed lane issues the tcgen05 instructions.
     {
-      const bool issuer = (lane == 0);
+      PROF_DECL
+#ifdef SPB_PROFILE
+      const unsigned long long prof_start = clock64();
+#endif
+      unsigned long long prof_w = 0;
+      const bool issuer = elect_one();
       const uint32_t b_lo_base = ((s_base + Sm::OFF_W) >> 4);
       uint32_t use = 0;        // layer-uses of the weight ring so far
       uint32_t act_par = 0;    // bit t: parity of the next completion of act_ready[t]
+      uint32_t stage_par = 0;  // same for stage_ready[t]
       for (uint32_t b = 0; b < n_batches; ++b) {
         const uint32_t nb = min((uint32_t)Ge::NB, my_end - my_begin - b * Ge::NB);
         const int nt = (int)((nb * Ge::BS + 127) / 128);
         for (int l = 0; l < N_LAYERS; ++l) {
           const uint32_t in_buf = s_base + ((l == 0 || (l >= 2 && (l & 1) == 0)) ? Sm::OFF_ACT0 : Sm::OFF_ACT1);
           const uint32_t a_lo_base = ((in_buf >> 4) + Ge::LEAD) | ((uint32_t)Ge::Q << 16);
-          const uint32_t cur_par = act_par;
-          act_par ^= (1u << nt) - 1u;
+          const uint32_t cur_par = (l == 0) ? stage_par : act_par;
+          if (l == 0) stage_par ^= (1u << nt) - 1u; else act_par ^= (1u << nt) - 1u;
           for (int t = 0; t < nt; ++t) {
             const int wt = min(t + 1, nt - 1);                   // epilogue runs tiles in order: tile wt done => 0..wt done
-            mbar_wait(bar_act_ready(wt), (cur_par >> wt) & 1u);
+            PROF_BEGIN();
+            mbar_wait(l == 0 ? bar_stage_ready(wt) : bar_act_ready(wt), (cur_par >> wt) & 1u);
+            PROF_END(prof_acc0);
+#ifdef SPB_PROFILE
+            if (lane == 0) g_eval_prof_layer[blockIdx.x][l] += clock64() - prof_t0;
+            const unsigned long long w_before = prof_w;
+#endif
             tc_fence_after();
             const uint32_t a_lo_tile = a_lo_base + (uint32_t)t * 128u;
-            const uint32_t d_tmem = tmem_base + (uint32_t)t * 64u;
+            const uint32_t d_tmem = tmem_base + (b & 1u) * 256u + (uint32_t)t * 64u;   // accumulators ping-pong per batch
             const bool first = (t == 0), last = (t == nt - 1);
             if (l == 0)
-              issue_tile<Ge::W8, Ge::Q, 1, 64>(issuer, a_lo_tile, b_lo_base, 2048 >> 4, d_tmem, first, last, use & 1u, bar_base);
+              issue_tile<Ge::W8, Ge::Q, 1, 64>(issuer, a_lo_tile, b_lo_base, 2048 >> 4, d_tmem, first, last, use & 1u, bar_base, prof_w);
             else if (l < 9)
-              issue_tile<Ge::W8, Ge::Q, 4, 64>(issuer, a_lo_tile, b_lo_base, SLOT_BYTES >> 4, d_tmem, first, last, use & 1u, bar_base);
+              issue_tile<Ge::W8, Ge::Q, 4, 64>(issuer, a_lo_tile, b_lo_base, SLOT_BYTES >> 4, d_tmem, first, last, use & 1u, bar_base, prof_w);
             else
-              issue_tile<Ge::W8, Ge::Q, 4, HEAD_N>(issuer, a_lo_tile, b_lo_base, SLOT_BYTES >> 4, d_tmem, first, last, use & 1u, bar_base);
-            if (issuer) umma_commit(bar_acc_full(t));
+              issue_tile<Ge::W8, Ge::Q, 4, HEAD_N>(issuer, a_lo_tile, b_lo_base, SLOT_BYTES >> 4, d_tmem, first, last, use & 1u, bar_base, prof_w);
+#ifdef SPB_PROFILE
+            if (lane == 0) g_eval_prof_layer[blockIdx.x][10 + l] += prof_w - w_before;
+#endif
+            if (issuer) umma_commit(bar_acc_full(b & 1u, t));
             __syncwarp();
           }
           ++use;
         }
       }
+#ifdef SPB_PROFILE
+      if (lane == 0) {
+        g_eval_prof[blockIdx.x][0] = clock64() - prof_start;   // MMA warp total
+        g_eval_prof[blockIdx.x][1] = prof_acc0;                // waiting for activations (epilogue)
+        g_eval_prof[blockIdx.x][2] = n_batches;
+        g_eval_prof[blockIdx.x][5] = prof_w;                    // waiting for weights (TMA ring)
+      }
+#endif
     }
   } else {
-    // ===== epilogue warps (128 threads): encode, per-layer epilogues, heads ============================
-    const int et = tid - 64;                                       // 0..127
+    // ===== epilogue warps (8 warps, 256 threads): encode, per-layer epilogues, heads ====================
+    // Two warps share a TMEM lane quadrant (a tile row) and split the 64 output channels in halves.
+    const int et = tid - 64;                                       // 0..255
     const int quad = warp & 3;                                     // TMEM lanes [32*quad, 32*quad+32)
+    const int half = (warp - 2) >> 2;                              // channels [32*half, 32*half+32)
     const int row_in_tile = quad * 32 + lane;
     const float* s_bias = reinterpret_cast<const float*>(smem + Sm::OFF_BIAS);
     float* s_logits = reinterpret_cast<float*>(smem + Sm::OFF_LOGITS);
+    float* s_part = reinterpret_cast<float*>(smem + Sm::OFF_PART);
     PState* s_states = reinterpret_cast<PState*>(smem + Sm::OFF_STATES);
     uint32_t* s_slots = reinterpret_cast<uint32_t*>(smem + Sm::OFF_SLOTS);
     const uint16_t* g_wp = reinterpret_cast<const uint16_t*>(image + OFF_WP);
     const float* g_wv = reinterpret_cast<const float*>(image + off_wv<G>());
     const float* g_fcb = reinterpret_cast<const float*>(image + off_fcb<G>());
-    uint32_t acc_par = 0;                                          // bit t: parity of the next completion of acc_full[t]
+    constexpr int PCH = (G::A + 1 + 3) / 4;                        // 16-B chunks of head partial sums per half
+    uint32_t acc_par[2] = {0, 0};                                  // [set] bit t: parity of the next completion of acc_full[set][t]
+    PROF_DECL
+#ifdef SPB_PROFILE
+    const unsigned long long prof_start = clock64();
+#endif
+
+    // Fetches the states of batch `bb` and writes their encoding (get_encoding, connect_four.rs:242-259: channels
+    // 0,1,2 of chunk 0; chunk 1 = 0) into activation buffer 0, then releases the stem MMAs.  Called for batch b+1
+    // while the tensor pipe runs the head conv of batch b, so the pipe never waits for a batch turn-around.
+    auto stage_batch = [&](uint32_t bb) {
+      const uint32_t b0 = my_begin + bb * Ge::NB;
+      const uint32_t nb = min((uint32_t)Ge::NB, my_end - b0);
+      const int nt = (int)((nb * Ge::BS + 127) / 128);
+      PState* st_buf = s_states + (bb & 1u) * Ge::NB;
+      uint32_t* sl_buf = s_slots + (bb & 1u) * Ge::NB;
+      if ((uint32_t)et < nb) {
+        const uint32_t slot = list ? list[b0 + et] : (b0 + et);
+        sl_buf[et] = slot;
+        st_buf[et] = states[slot];
+      }
+      epi_bar_sync();
+      for (int t = 0; t < nt; ++t) {
+        const int m = t * 128 + row_in_tile;
+        const int bi = m / Ge::BS, rem = m % Ge::BS, r = rem / Ge::W8, c = rem % Ge::W8;
+        uint4 v0 = make_uint4(0, 0, 0, 0);
+        if (half == 0 && (uint32_t)bi < nb && r < G::ROWS && c < G::COLS) {
+          const PState st = st_buf[bi];
+          const float e0 = G::encode_cell(st, 0, r, c), e1 = G::encode_cell(st, 1, r, c), e2 = G::encode_cell(st, 2, r, c);
+          v0.x = pack_bf16x2(e0, e1);
+          v0.y = pack_bf16x2(e2, 0.0f);
+        }
+        *reinterpret_cast<uint4*>(smem + Sm::OFF_ACT0 + (size_t)half * Ge::Q * 16 + (size_t)(Ge::LEAD + m) * 16) = v0;
+        fence_async_smem();
+        mbar_arrive(bar_stage_ready(t));
+      }
+    };
+    stage_batch(0);
 
     for (uint32_t b = 0; b < n_batches; ++b) {
       const uint32_t b0 = my_begin + b * Ge::NB;
       const uint32_t nb = min((uint32_t)Ge::NB, my_end - b0);
       const int nt = (int)((nb * Ge::BS + 127) / 128);
-      // ---- batch prologue: fetch states, clear head accumulators
-      if ((uint32_t)et < nb) {
-        const uint32_t slot = list ? list[b0 + et] : (b0 + et);
-        s_slots[et] = slot;
-        s_states[et] = states[slot];
-      }
-      epi_bar_sync();
-      // ---- encode (get_encoding, connect_four.rs:242-259): channels 0,1,2 of chunk 0; chunk 1 = 0
-      for (int t = 0; t < nt; ++t) {
-        const int m = t * 128 + row_in_tile;
-        const int bi = m / Ge::BS, rem = m % Ge::BS, r = rem / Ge::W8, c = rem % Ge::W8;
-        uint4 v0 = make_uint4(0, 0, 0, 0);
-        if ((uint32_t)bi < nb && r < G::ROWS && c < G::COLS) {
-          const PState st = s_states[bi];
-          const float e0 = G::encode_cell(st, 0, r, c), e1 = G::encode_cell(st, 1, r, c), e2 = G::encode_cell(st, 2, r, c);
-          v0.x = pack_bf16x2(e0, e1);
-          v0.y = pack_bf16x2(e2, 0.0f);
-        }
-        uint8_t* dst = smem + Sm::OFF_ACT0 + (size_t)(Ge::LEAD + m) * 16;
-        *reinterpret_cast<uint4*>(dst) = v0;
-        *reinterpret_cast<uint4*>(dst + (size_t)Ge::Q * 16) = make_uint4(0, 0, 0, 0);
-        fence_async_smem();
-        mbar_arrive(bar_act_ready(t));
-      }
+      const uint32_t tmem_acc = tmem_base + (b & 1u) * 256u;
+      const uint32_t* sl_cur = s_slots + (b & 1u) * Ge::NB;
       // ---- layers
       for (int l = 0; l < N_LAYERS; ++l) {
         const bool in0 = (l == 0 || (l >= 2 && (l & 1) == 0));
         uint8_t* dst_buf = smem + (in0 ? Sm::OFF_ACT1 : Sm::OFF_ACT0);
         const bool has_skip = (l >= 2 && (l & 1) == 0 && l <= 8);   // second conv of a residual block
-        const float* bias = s_bias + l * 64;
-        const uint32_t cur_par = acc_par;
-        acc_par ^= (1u << nt) - 1u;
-        for (int t = 0; t < nt; ++t) {
-          mbar_wait(bar_acc_full(t), (cur_par >> t) & 1u);
-          tc_fence_after();
-          const int m = t * 128 + row_in_tile;
-          const int bi = m / Ge::BS, rem = m % Ge::BS, r = rem / Ge::W8, c = rem % Ge::W8;
-          const bool valid = (uint32_t)bi < nb && r < G::ROWS && c < G::COLS;
-          const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)t * 64u;
-          if (l < 9) {
-            uint8_t* drow = dst_buf + (size_t)(Ge::LEAD + m) * 16;
+        const uint32_t cur_par = acc_par[b & 1u];
+        acc_par[b & 1u] ^= (1u << nt) - 1u;
+        if (l < 9) {
+          float bias_r[32];                                         // this thread's 32 output channels
 #pragma unroll
-            for (int half = 0; half < 4; ++half) {                 // 16 output channels at a time
-              uint32_t a[16];
-              tmem_ld16(taddr + half * 16, a);
-              tmem_ld_wait();
+          for (int q = 0; q < 8; ++q) {
+            const float4 bv = *reinterpret_cast<const float4*>(s_bias + l * 64 + half * 32 + q * 4);
+            bias_r[4 * q] = bv.x; bias_r[4 * q + 1] = bv.y; bias_r[4 * q + 2] = bv.z; bias_r[4 * q + 3] = bv.w;
+          }
+          for (int t = 0; t < nt; ++t) {
+            const int m = t * 128 + row_in_tile;
+            const int bi = m / Ge::BS, rem = m % Ge::BS, r = rem / Ge::W8, c = rem % Ge::W8;
+            const bool valid = (uint32_t)bi < nb && r < G::ROWS && c < G::COLS;
+            uint8_t* drow = dst_buf + (size_t)(half * 4) * Ge::Q * 16 + (size_t)(Ge::LEAD + m) * 16;   // chunk 4*half
+            uint4 sk[4];
+            if (has_skip) {                                         // (x + f(x)).relu(), model/mod.rs:163
 #pragma unroll
-              for (int j = 0; j < 2; ++j) {                        // one 8-channel chunk = one 16-B store
-                const int ch0 = half * 16 + j * 8;
-                float v[8];
+              for (int j = 0; j < 4; ++j) sk[j] = *reinterpret_cast<const uint4*>(drow + (size_t)j * Ge::Q * 16);
+            }
+            PROF_BEGIN();
+            mbar_wait(bar_acc_full(b & 1u, t), (cur_par >> t) & 1u);
+            PROF_END(prof_acc0);
+            tc_fence_after();
+            const uint32_t taddr = tmem_acc + ((uint32_t)(quad * 32) << 16) + (uint32_t)t * 64u + (uint32_t)half * 32u;
+            uint32_t a[32];
+            tmem_ld16(taddr, a);
+            tmem_ld16(taddr + 16, a + 16);
+            tmem_ld_wait();
 #pragma unroll
-                for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(a[j * 8 + e]) + bias[ch0 + e];
-                uint8_t* p = drow + (size_t)(ch0 / 8) * Ge::Q * 16;
-                if (has_skip) {                                    // (x + f(x)).relu(), model/mod.rs:163
-                  const uint4 sk = *reinterpret_cast<const uint4*>(p);
-                  v[0] += bf_lo(sk.x); v[1] += bf_hi(sk.x); v[2] += bf_lo(sk.y); v[3] += bf_hi(sk.y);
-                  v[4] += bf_lo(sk.z); v[5] += bf_hi(sk.z); v[6] += bf_lo(sk.w); v[7] += bf_hi(sk.w);
-                }
-                uint4 o = make_uint4(0, 0, 0, 0);
-                if (valid) {
-                  o.x = pack_bf16x2(fmaxf(v[0], 0.f), fmaxf(v[1], 0.f));
-                  o.y = pack_bf16x2(fmaxf(v[2], 0.f), fmaxf(v[3], 0.f));
-                  o.z = pack_bf16x2(fmaxf(v[4], 0.f), fmaxf(v[5], 0.f));
-                  o.w = pack_bf16x2(fmaxf(v[6], 0.f), fmaxf(v[7], 0.f));
-                }
-                *reinterpret_cast<uint4*>(p) = o;
+            for (int j = 0; j < 4; ++j) {                           // one 8-channel chunk = one 16-B store
+              float v[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(a[j * 8 + e]) + bias_r[j * 8 + e];
+              if (has_skip) {
+                v[0] += bf_lo(sk[j].x); v[1] += bf_hi(sk[j].x); v[2] += bf_lo(sk[j].y); v[3] += bf_hi(sk[j].y);
+                v[4] += bf_lo(sk[j].z); v[5] += bf_hi(sk[j].z); v[6] += bf_lo(sk[j].w); v[7] += bf_hi(sk[j].w);
               }
+              uint4 o = make_uint4(0, 0, 0, 0);
+              if (valid) {
+                o.x = pack_bf16x2(fmaxf(v[0], 0.f), fmaxf(v[1], 0.f));
+                o.y = pack_bf16x2(fmaxf(v[2], 0.f), fmaxf(v[3], 0.f));
+                o.z = pack_bf16x2(fmaxf(v[4], 0.f), fmaxf(v[5], 0.f));
+                o.w = pack_bf16x2(fmaxf(v[6], 0.f), fmaxf(v[7], 0.f));
+              }
+              *reinterpret_cast<uint4*>(drow + (size_t)j * Ge::Q * 16) = o;
             }
             fence_async_smem();
             tc_fence_before();
             mbar_arrive(bar_act_ready(t));
-          } else {
-            // ---- heads: policy conv channels 0..31, value conv channels 32..34, then the two Linear layers
-            float pl[Ge::APAD + 4];
-#pragma unroll
-            for (int a = 0; a < Ge::APAD + 4; ++a) pl[a] = 0.0f;
-            float vl = 0.0f;
+          }
+        } else {
+          // The head conv's MMAs are in flight: stage the next batch now (buffer 0 is no longer read by this batch).
+          if (b + 1 < n_batches) stage_batch(b + 1);
+          // ---- heads: policy conv channels 0..31 (16 per half), value conv channels 32..34 (half 1), then the
+          // per-position terms of the two Linear layers.
+          const float* bias = s_bias + l * 64;
+          for (int t = 0; t < nt; ++t) {
+            const int m = t * 128 + row_in_tile;
+            const int bi = m / Ge::BS, rem = m % Ge::BS, r = rem / Ge::W8, c = rem % Ge::W8;
+            const bool valid = (uint32_t)bi < nb && r < G::ROWS && c < G::COLS;
             const int pos = r * G::COLS + c;
+            // prefetch this position's policy-Linear weights (bf16 [pos][ch][APAD]) before waiting for the MMA
+            uint4 w[16 * (Ge::APAD / 8)];
+            if (valid) {
+              const uint4* wrow = reinterpret_cast<const uint4*>(g_wp + ((size_t)pos * NET_POLICY_CH + half * 16) * Ge::APAD);
 #pragma unroll
-            for (int part = 0; part < 3; ++part) {
-              uint32_t a[16];
-              tmem_ld16(taddr + part * 16, a);
-              tmem_ld_wait();
-              if (valid) {
-                if (part < 2) {
+              for (int i = 0; i < 16 * (Ge::APAD / 8); ++i) w[i] = __ldg(wrow + i);
+            }
+            PROF_BEGIN();
+            mbar_wait(bar_acc_full(b & 1u, t), (cur_par >> t) & 1u);
+            PROF_END(prof_acc0);
+            tc_fence_after();
+            const uint32_t taddr = tmem_acc + ((uint32_t)(quad * 32) << 16) + (uint32_t)t * 64u;
+            uint32_t a[16], av[16];
+            tmem_ld16(taddr + (uint32_t)half * 16u, a);
+            if (half == 1) tmem_ld16(taddr + 32u, av);
+            tmem_ld_wait();
+            tc_fence_before();
+            if (valid) {
+              float pl[Ge::APAD + 4];
 #pragma unroll
-                  for (int e = 0; e < 16; ++e) {
-                    const int ch = part * 16 + e;
-                    const float act = fmaxf(__uint_as_float(a[e]) + bias[ch], 0.0f);
-                    const uint4* wrow = reinterpret_cast<const uint4*>(g_wp + ((size_t)pos * NET_POLICY_CH + ch) * Ge::APAD);
+              for (int i = 0; i < Ge::APAD + 4; ++i) pl[i] = 0.0f;
 #pragma unroll
-                    for (int q = 0; q < Ge::APAD / 8; ++q) {
-                      const uint4 w = __ldg(wrow + q);
-                      pl[q * 8 + 0] = fmaf(act, bf_lo(w.x), pl[q * 8 + 0]); pl[q * 8 + 1] = fmaf(act, bf_hi(w.x), pl[q * 8 + 1]);
-                      pl[q * 8 + 2] = fmaf(act, bf_lo(w.y), pl[q * 8 + 2]); pl[q * 8 + 3] = fmaf(act, bf_hi(w.y), pl[q * 8 + 3]);
-                      pl[q * 8 + 4] = fmaf(act, bf_lo(w.z), pl[q * 8 + 4]); pl[q * 8 + 5] = fmaf(act, bf_hi(w.z), pl[q * 8 + 5]);
-                      pl[q * 8 + 6] = fmaf(act, bf_lo(w.w), pl[q * 8 + 6]); pl[q * 8 + 7] = fmaf(act, bf_hi(w.w), pl[q * 8 + 7]);
-                    }
-                  }
-                } else {
-                  const float4 wv = __ldg(reinterpret_cast<const float4*>(g_wv) + pos);
-                  vl = fmaf(fmaxf(__uint_as_float(a[0]) + bias[32], 0.0f), wv.x, vl);
-                  vl = fmaf(fmaxf(__uint_as_float(a[1]) + bias[33], 0.0f), wv.y, vl);
-                  vl = fmaf(fmaxf(__uint_as_float(a[2]) + bias[34], 0.0f), wv.z, vl);
+              for (int e = 0; e < 16; ++e) {
+                const float act = fmaxf(__uint_as_float(a[e]) + bias[half * 16 + e], 0.0f);
+#pragma unroll
+                for (int q = 0; q < Ge::APAD / 8; ++q) {
+                  const uint4 wq = w[e * (Ge::APAD / 8) + q];
+                  pl[q * 8 + 0] = fmaf(act, bf_lo(wq.x), pl[q * 8 + 0]); pl[q * 8 + 1] = fmaf(act, bf_hi(wq.x), pl[q * 8 + 1]);
+                  pl[q * 8 + 2] = fmaf(act, bf_lo(wq.y), pl[q * 8 + 2]); pl[q * 8 + 3] = fmaf(act, bf_hi(wq.y), pl[q * 8 + 3]);
+                  pl[q * 8 + 4] = fmaf(act, bf_lo(wq.z), pl[q * 8 + 4]); pl[q * 8 + 5] = fmaf(act, bf_hi(wq.z), pl[q * 8 + 5]);
+                  pl[q * 8 + 6] = fmaf(act, bf_lo(wq.w), pl[q * 8 + 6]); pl[q * 8 + 7] = fmaf(act, bf_hi(wq.w), pl[q * 8 + 7]);
                 }
               }
-            }
-            if (valid) {
-              // Per-position partial sums go to this row's own (now dead) cells of activation buffer 0, chunks
-              // 2.. — pad rows stay zero, and every chunk >= 2 is rewritten by layer 1 before it is read again.
+              float vl = 0.0f;
+              if (half == 1) {
+                const float4 wv = __ldg(reinterpret_cast<const float4*>(g_wv) + pos);
+                vl = fmaf(fmaxf(__uint_as_float(av[0]) + bias[32], 0.0f), wv.x, vl);
+                vl = fmaf(fmaxf(__uint_as_float(av[1]) + bias[33], 0.0f), wv.y, vl);
+                vl = fmaf(fmaxf(__uint_as_float(av[2]) + bias[34], 0.0f), wv.z, vl);
+              }
               pl[G::A] = vl;
+              // Per-position partial sums go to this row's own (now dead) cells of activation buffer 0: chunks
+              // 2+PCH*half.. — pad rows stay zero, and every chunk >= 2 is rewritten by layer 1 before it is read again.
               uint8_t* prow = smem + Sm::OFF_ACT0 + (size_t)(Ge::LEAD + m) * 16;
 #pragma unroll
-              for (int q = 0; q < (G::A + 1 + 3) / 4; ++q)
-                *reinterpret_cast<float4*>(prow + (size_t)(2 + q) * Ge::Q * 16) = make_float4(pl[4 * q], pl[4 * q + 1], pl[4 * q + 2], pl[4 * q + 3]);
+              for (int q = 0; q < PCH; ++q)
+                *reinterpret_cast<float4*>(prow + (size_t)(2 + PCH * half + q) * Ge::Q * 16) = make_float4(pl[4 * q], pl[4 * q + 1], pl[4 * q + 2], pl[4 * q + 3]);
             }
-            tc_fence_before();
           }
         }
       }
-      // ---- finish the batch: softmax (model/mod.rs:63) and tanh (connect_four.rs:71), one thread per board
+      // ---- finish the batch
       epi_bar_sync();
       // Linear layers: sum the per-position partials of each board in a FIXED order (deterministic results,
-      // independent of how leaves were batched): thread <-> (board, output).
-      for (int i = et; i < (int)nb * 16; i += 128) {
+      // independent of how leaves were batched), in two levels: (board, row, output) over the columns and both
+      // channel halves, then (board, output) over the rows.
+      for (int i = et; i < (int)nb * G::ROWS * 16; i += 256) {
+        const int a = i & 15, br = i >> 4, bi = br / G::ROWS, r = br % G::ROWS;
+        if (a <= G::A) {
+          float acc = 0.0f;
+#pragma unroll
+          for (int c = 0; c < G::COLS; ++c) {
+            const uint8_t* prow = smem + Sm::OFF_ACT0 + (size_t)(Ge::LEAD + bi * Ge::BS + r * Ge::W8 + c) * 16 + (a & 3) * 4;
+            acc += *reinterpret_cast<const float*>(prow + (size_t)(2 + (a >> 2)) * Ge::Q * 16);
+            acc += *reinterpret_cast<const float*>(prow + (size_t)(2 + PCH + (a >> 2)) * Ge::Q * 16);
+          }
+          s_part[br * 16 + a] = acc;
+        }
+      }
+      epi_bar_sync();
+      for (int i = et; i < (int)nb * 16; i += 256) {
         const int bi = i >> 4, a = i & 15;
         if (a <= G::A) {
           float acc = 0.0f;
-          for (int r = 0; r < G::ROWS; ++r)
-            for (int c = 0; c < G::COLS; ++c) {
-              const int m = bi * Ge::BS + r * Ge::W8 + c;
-              acc += *reinterpret_cast<const float*>(smem + Sm::OFF_ACT0 + (size_t)(2 + (a >> 2)) * Ge::Q * 16 + (size_t)(Ge::LEAD + m) * 16 + (a & 3) * 4);
-            }
+#pragma unroll
+          for (int r = 0; r < G::ROWS; ++r) acc += s_part[(bi * G::ROWS + r) * 16 + a];
           s_logits[bi * 16 + (a == G::A ? 15 : a)] = acc;
         }
       }
       epi_bar_sync();
+      // softmax (model/mod.rs:63) and tanh (connect_four.rs:71), one thread per board
       if ((uint32_t)et < nb) {
-        const uint32_t slot = s_slots[et];
+        const uint32_t slot = sl_cur[et];
         float lg[G::A];
         float mx = -INFINITY;
 #pragma unroll
@@ -518,12 +633,18 @@ k_eval_umma(const uint8_t* __restrict__ image, const PState* __restrict__ states
       }
       epi_bar_sync();                                              // s_logits / s_states are reused by the next batch
     }
+#ifdef SPB_PROFILE
+    if (et == 0) {
+      g_eval_prof[blockIdx.x][3] = clock64() - prof_start;     // epilogue warp total
+      g_eval_prof[blockIdx.x][4] = prof_acc0;                  // waiting for accumulators (MMA)
+    }
+#endif
   }
 
   // ---- teardown -----------------------------------------------------------------------------------
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 256); }
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
 template <class G>
@@ -544,6 +665,18 @@ static cudaError_t launch_t(const Evaluator::DevNet& net, const PState* states, 
                                                             out, stride, logits_out);
   return cudaGetLastError();
 }
+
+#ifdef SPB_PROFILE
+extern "C" int spb_debug_set(int v) { return (int)cudaMemcpyToSymbol(g_eval_debug, &v, sizeof v); }
+extern "C" int spb_debug_eval_profile_layers(unsigned long long* out, int n_ctas, int reset) {
+  int rc = (int)cudaMemcpyFromSymbol(out, g_eval_prof_layer, sizeof(unsigned long long) * 24 * (size_t)n_ctas);
+  if (reset) { static unsigned long long z[160 * 24]; rc |= (int)cudaMemcpyToSymbol(g_eval_prof_layer, z, sizeof z); }
+  return rc;
+}
+extern "C" int spb_debug_eval_profile(unsigned long long* out, int n_ctas) {
+  return (int)cudaMemcpyFromSymbol(out, g_eval_prof, sizeof(unsigned long long) * 8 * (size_t)n_ctas);
+}
+#endif
 
 cudaError_t launch(const Evaluator::DevNet& net, int game, const PState* states, const uint32_t* list, const uint32_t* count_dev,
                    uint32_t max_n, float* out, int stride, float* logits_out, cudaStream_t stream) {
