@@ -84,7 +84,8 @@ typedef struct spb_config {
   int32_t  device;               /* CUDA device ordinal */
   uint32_t num_games;            /* G: concurrent trees ("slots"); ref: mcts.rs:54 num_parallel_self_play_games */
   uint32_t max_nodes_per_tree;   /* arena capacity per tree; 0 = default (16384) */
-  uint32_t leaves_per_tree;      /* K in-flight leaves per tree per step; 1 = the reference algorithm */
+  uint32_t leaves_per_tree;      /* K in-flight leaves per tree per step (1..16); 1 = the reference algorithm.
+                                    K > 1 is an EXTENSION (virtual loss, defined in DESIGN.md §4.4): not in the reference */
   float    c;                    /* PUCT constant; ref: mcts.rs:49 (2.0) */
   int32_t  evaluator;            /* SPB_EVAL_* */
   uint32_t flags;                /* SPB_FLAG_* */

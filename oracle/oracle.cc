@@ -480,6 +480,84 @@ void search(std::vector<Tree<S>*>& trees, uint32_t num_searches, const Evaluator
   }
 }
 
+// ---- EXTENSION (not in the reference): K in-flight leaves per tree with virtual loss --------------------
+// BASELINE.json config 4 / SURVEY.md §8(f)-3.  The reference runs exactly one leaf per tree per step
+// (mcts.rs:236-252); with K = 1 this function is never used and the reference algorithm above is.  Definition
+// (the device kernels implement exactly the same operation order):
+//   a step performs k_this = min(K, remaining) simulations per tree.  Simulation k descends with PUCT on the
+//   current statistics.  Terminal leaf: real backprop at once.  Otherwise every node of the path gets a
+//   virtual loss (visit_count += 1, value_sum += 1.0) and the leaf is queued; if the same leaf was already
+//   queued in this step the simulation is a duplicate of that entry (it still takes its virtual loss).
+//   After the batch evaluation, entries are finished in selection order: a first occurrence expands the leaf;
+//   every entry then rewrites each path node as value_sum = (value_sum - 1.0) + sign*v (the visit stays).
+template <class S>
+void search_vl(std::vector<Tree<S>*>& trees, uint32_t num_searches, uint32_t K, const Evaluator<S>& ev, Counters& ctr) {
+  constexpr int A = S::A;
+  struct Entry { size_t leaf; int dup_of; std::vector<size_t> path; };
+  std::vector<std::vector<Entry>> pending(trees.size());
+  std::vector<const S*> states;
+  std::vector<std::pair<size_t, size_t>> owners;   // (tree index, entry index) per evaluated state
+  std::vector<float> policies, values;
+  uint32_t done = 0;
+  while (done < num_searches) {
+    const uint32_t k_this = std::min(K, num_searches - done);
+    states.clear(); owners.clear();
+    for (size_t ti = 0; ti < trees.size(); ++ti) {
+      Tree<S>* tree = trees[ti];
+      auto& pend = pending[ti];
+      pend.clear();
+      for (uint32_t k = 0; k < k_this; ++k) {
+        std::vector<size_t> path{0};
+        size_t node = 0;
+        while (tree->arena[node].is_fully_expanded()) {
+          node = tree->select(node);
+          path.push_back(node);
+          ctr.path_length_sum++;
+        }
+        ctr.simulations++;
+        float value; bool is_terminal;
+        tree->arena[node].state.get_value_and_terminated(&value, &is_terminal);
+        if (is_terminal) {
+          tree->backprop(node, value);
+          ctr.terminal_leaves++;
+          continue;
+        }
+        int dup = -1;
+        for (size_t j = 0; j < pend.size(); ++j)
+          if (pend[j].dup_of < 0 && pend[j].leaf == node) { dup = (int)j; break; }
+        for (size_t id : path) { tree->arena[id].visit_count += 1; tree->arena[id].value_sum += 1.0f; }   // virtual loss
+        pend.push_back(Entry{node, dup, path});
+        if (dup < 0) { states.push_back(&tree->arena[node].state); owners.emplace_back(ti, pend.size() - 1); }
+      }
+    }
+    if (!states.empty()) {
+      ev.predict(states, policies, values);
+      ctr.evaluations += states.size();
+      std::vector<std::vector<float>> val_of(trees.size());
+      std::vector<std::vector<const float*>> pol_of(trees.size());
+      for (size_t ti = 0; ti < trees.size(); ++ti) { val_of[ti].assign(pending[ti].size(), 0.0f); pol_of[ti].assign(pending[ti].size(), nullptr); }
+      for (size_t i = 0; i < owners.size(); ++i) { val_of[owners[i].first][owners[i].second] = values[i]; pol_of[owners[i].first][owners[i].second] = &policies[i * A]; }
+      for (size_t ti = 0; ti < trees.size(); ++ti) {
+        Tree<S>* tree = trees[ti];
+        auto& pend = pending[ti];
+        for (size_t e = 0; e < pend.size(); ++e) {
+          const size_t src = pend[e].dup_of < 0 ? e : (size_t)pend[e].dup_of;
+          if (pend[e].dup_of < 0) tree->expand(pend[e].leaf, pol_of[ti][e], ctr);
+          const float v = val_of[ti][src];
+          const auto& path = pend[e].path;
+          float sign = 1.0f;
+          for (size_t d = path.size(); d-- > 0;) {          // leaf first (+v), then parents with alternating sign
+            Node<S>& nd = tree->arena[path[d]];
+            nd.value_sum = (nd.value_sum - 1.0f) + sign * v;
+            sign *= -1.0f;
+          }
+        }
+      }
+    }
+    done += k_this;
+  }
+}
+
 struct ForestBase {
   std::string err;
   int game;
@@ -493,12 +571,14 @@ struct ForestBase {
   virtual int32_t arena_len(uint32_t slot, uint32_t*) = 0;
   virtual int32_t node_stats(uint32_t, uint32_t, uint32_t*, float*, float*, uint32_t*, uint32_t*) = 0;
   virtual void counters(spb_counters*) = 0;
+  virtual void set_leaves_per_tree(uint32_t k) = 0;
 };
 
 template <class S>
 struct Forest : ForestBase {
   std::vector<Tree<S>> trees;
   float c;
+  uint32_t K = 1;
   Counters ctr;
   Forest(uint32_t n, float c_) : trees(n), c(c_) { game = S::GAME; for (auto& t : trees) t.c = c; }
   bool ok(uint32_t slot) { if (slot >= trees.size()) { err = "slot out of range"; return false; } return true; }
@@ -516,7 +596,7 @@ struct Forest : ForestBase {
     std::vector<Tree<S>*> ptrs;
     for (auto& t : trees) ptrs.push_back(&t);
     Evaluator<S> ev{kind, fn, user};
-    search(ptrs, s, ev, ctr);
+    if (K <= 1) search(ptrs, s, ev, ctr); else search_vl(ptrs, s, K, ev, ctr);
     return SPB_OK;
   }
   // mcts.rs:310-331
@@ -572,6 +652,7 @@ struct Forest : ForestBase {
     if (nc) *nc = (uint32_t)nd.children_ids.size();
     return SPB_OK;
   }
+  void set_leaves_per_tree(uint32_t k) override { K = k; }
   void counters(spb_counters* out) override {
     std::memset(out, 0, sizeof *out);
     out->simulations = ctr.simulations;
@@ -661,6 +742,7 @@ int32_t orc_node_stats(orc_forest* f, uint32_t slot, uint32_t node, uint32_t* n,
   return f->impl->node_stats(slot, node, n, w, p, fc, nc);
 }
 int32_t orc_get_counters(orc_forest* f, spb_counters* out) { f->impl->counters(out); return SPB_OK; }
+int32_t orc_set_leaves_per_tree(orc_forest* f, uint32_t k) { if (k < 1 || k > 16) return SPB_ERR_ARG; f->impl->set_leaves_per_tree(k); return SPB_OK; }
 
 int32_t orc_next_state(int32_t game, const spb_state* s, uint8_t action, spb_state* out) {
   if (game == SPB_GAME_CONNECT4) {

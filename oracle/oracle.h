@@ -48,6 +48,8 @@ int32_t orc_arena_len(orc_forest* f, uint32_t slot, uint32_t* out);
 int32_t orc_node_stats(orc_forest* f, uint32_t slot, uint32_t node_id, uint32_t* visit_count,
                        float* value_sum, float* prior, uint32_t* first_child, uint32_t* n_children);
 int32_t orc_get_counters(orc_forest* f, spb_counters* out);
+/* EXTENSION (not in the reference): K in-flight leaves per tree per step with virtual loss; 1 = reference algorithm. */
+int32_t orc_set_leaves_per_tree(orc_forest* f, uint32_t k);
 
 /* State trait, one call per state (array-board restatement). */
 int32_t orc_next_state(int32_t game, const spb_state* s, uint8_t action, spb_state* out);

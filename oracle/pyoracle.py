@@ -95,6 +95,7 @@ def lib():
         L.orc_arena_len.argtypes = [C.c_void_p, C.c_uint32, u32p]
         L.orc_node_stats.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, u32p, f32p, f32p, u32p, u32p]
         L.orc_get_counters.argtypes = [C.c_void_p, C.POINTER(Counters)]
+        L.orc_set_leaves_per_tree.argtypes = [C.c_void_p, C.c_uint32]
         L.orc_next_state.argtypes = [C.c_int32, sp, C.c_uint8, sp]
         L.orc_valid_actions.restype = C.c_uint32
         L.orc_valid_actions.argtypes = [C.c_int32, sp]
@@ -192,11 +193,13 @@ def det_hash(game: int, s: State) -> int:
 class Forest:
     """`Vec<Tree>` + `Mcts::search` of the reference, restated on the CPU."""
 
-    def __init__(self, game: int, num_trees: int, c: float = 2.0):
+    def __init__(self, game: int, num_trees: int, c: float = 2.0, leaves_per_tree: int = 1):
         self.game, self.n, self.A = game, num_trees, NUM_ACTIONS[game]
         self._h = lib().orc_create(game, num_trees, c)
         if not self._h:
             raise ValueError("orc_create failed")
+        if leaves_per_tree != 1 and lib().orc_set_leaves_per_tree(self._h, leaves_per_tree) != 0:
+            raise ValueError("leaves_per_tree must be in 1..16")
 
     def close(self):
         if self._h:

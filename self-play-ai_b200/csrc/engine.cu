@@ -178,6 +178,123 @@ __global__ void __launch_bounds__(THREADS) k_tree_step(Trees T, int do_finish, i
   flush_counters(T, ctr, lane);
 }
 
+// ---- EXTENSION (not in the reference): K in-flight leaves per tree per step with virtual loss ------------
+// BASELINE.json config 4 / SURVEY.md §8(f)-3; the reference runs one leaf per tree per step (mcts.rs:236-252)
+// and K = 1 never comes here.  The warp that owns the tree runs its K descents one after the other, so no
+// atomics are needed and the result is deterministic.  Definition (identical in oracle/oracle.cc search_vl):
+//   select k: PUCT descent on the current statistics.  Terminal leaf: real backup at once.  Otherwise every
+//   path node takes a virtual loss (N += 1, W += 1.0) and the leaf is queued — as a duplicate if the same leaf
+//   is already queued in this step.  Finish (after the evaluator): entries in selection order; a first
+//   occurrence expands; every entry rewrites each path node as W = (W - 1.0) + sign*v.
+// leaf_info[slot]: depth[0,8) | LEAF_PENDING | LEAF_DUP | source entry[16,24)
+constexpr uint32_t LEAF_DUP = 1u << 9;
+
+__device__ __forceinline__ void backup_virtual(NodeRec* rec, const uint32_t* path, int depth, float v, int lane) {
+  for (int d = lane; d <= depth; d += 32) {
+    const uint32_t node = path[d];
+    const float sv = ((depth - d) & 1) ? -v : v;
+    float* w = &rec[node].W;
+    *w = __fadd_rn(__fsub_rn(*w, 1.0f), sv);
+  }
+}
+
+template <class G>
+__global__ void __launch_bounds__(THREADS) k_tree_step_multi(Trees T, int do_finish, uint32_t k_select, uint32_t parity) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t g = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  if (blockIdx.x == 0 && threadIdx.x == 0) T.eval_count[(parity + 1) & 1] = 0;
+  if (g >= T.G || !T.live[g]) return;
+  const uint32_t b = T.buf[g];
+  NodeRec* rec = T.rec[b] + (size_t)g * T.cap;
+  uint32_t* par = T.par[b] + (size_t)g * T.cap;
+  const uint32_t K = T.K;
+  unsigned long long ctr[CTR_COUNT] = {0, 0, 0, 0, 0};
+  bool ok = true;
+
+  if (do_finish) {
+    uint32_t n_nodes = T.n_nodes[g];
+    for (uint32_t k = 0; k < K && ok; ++k) {
+      const uint32_t slot = g * K + k;
+      const uint32_t li = T.leaf_info[slot];
+      if (!(li & (LEAF_PENDING | LEAF_DUP))) continue;
+      const int depth = (int)(li & 0xFFu);
+      const uint32_t src = (li & LEAF_DUP) ? g * K + ((li >> 16) & 0xFFu) : slot;
+      const uint32_t* pathm = T.path + (size_t)src * G::MAX_DEPTH;
+      const float* eo = T.eval_out + (size_t)src * G::EVAL_STRIDE;
+      if (li & LEAF_PENDING) {
+        float probs[G::A];
+#pragma unroll
+        for (int a = 0; a < G::A; ++a) probs[a] = eo[a];
+        const uint32_t before = n_nodes;
+        if (!expand<G>(rec, par, T.cap, n_nodes, pathm[depth], T.leaf_state[slot], probs, lane)) {
+          if (lane == 0) atomicOr(T.error, ERRBIT_POOL);
+          ok = false;
+          break;
+        }
+        ctr[CTR_CHILDREN] += n_nodes - before;
+      }
+      __syncwarp();
+      backup_virtual(rec, pathm, depth, eo[G::A], lane);
+      if (lane == 0) T.leaf_info[slot] = 0;
+      __syncwarp();
+    }
+    if (lane == 0) T.n_nodes[g] = n_nodes;
+  }
+
+  if (ok) {
+    uint32_t my_leaf = 0xFFFFFFFFu;                    // lane j: leaf queued by entry j of this step (first occurrences only)
+    const PState root = T.root_state[g];
+    for (uint32_t k = 0; k < k_select; ++k) {
+      const uint32_t slot = g * K + k;
+      WarpPath path;
+      uint32_t leaf, linfo;
+      int depth;
+      PState st;
+      descend<G>(rec, root, T.c, lane, path, leaf, depth, st, linfo, T.error);
+      ctr[CTR_SIMS] += 1;
+      ctr[CTR_PATHSUM] += (unsigned)depth;
+      const uint32_t status = info_status(linfo);
+      if (status != SPB_STATUS_ONGOING) {
+        ctr[CTR_TERMINAL] += 1;
+        backup_regs(rec, path, depth, terminal_value(status), lane);
+      } else {
+        const unsigned dupmask = __ballot_sync(0xffffffffu, my_leaf == leaf);
+        // virtual loss on the whole path (lane d <-> depth d)
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          const int d = lane + 32 * s;
+          if (d <= depth) {
+            uint2 nw;
+            nw.x = path.N[s] + 1u;
+            nw.y = __float_as_uint(__fadd_rn(path.W[s], 1.0f));
+            *reinterpret_cast<uint2*>(&rec[path.node[s]]) = nw;
+          }
+        }
+        if (dupmask) {
+          if (lane == 0) T.leaf_info[slot] = (uint32_t)depth | LEAF_DUP | ((uint32_t)(__ffs((int)dupmask) - 1) << 16);
+        } else {
+          ctr[CTR_EVALS] += 1;
+          uint32_t* pathm = T.path + (size_t)slot * G::MAX_DEPTH;
+#pragma unroll
+          for (int s = 0; s < 2; ++s) {
+            const int d = lane + 32 * s;
+            if (d <= depth) pathm[d] = path.node[s];
+          }
+          if (lane == (int)k) my_leaf = leaf;
+          if (lane == 0) {
+            T.leaf_state[slot] = st;
+            T.leaf_info[slot] = (uint32_t)depth | LEAF_PENDING;
+            const uint32_t pos = atomicAdd(&T.eval_count[parity & 1], 1u);
+            T.eval_list[pos] = slot;
+          }
+        }
+      }
+      __syncwarp();
+    }
+  }
+  flush_counters(T, ctr, lane);
+}
+
 // Evaluator stand-ins for the split pipeline (parity harness): DetEval / uniform over the work list.
 template <class G, int EVAL>
 __global__ void k_eval_builtin(const PState* states, const uint32_t* list, const uint32_t* count, float* out) {
@@ -639,7 +756,7 @@ template <class G>
 int32_t spb_engine::search_t(uint32_t num_searches) {
   if (num_searches == 0) return SPB_OK;
   const uint32_t blocks = (T.G + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
-  const bool split = cfg.evaluator == SPB_EVAL_NET || (cfg.flags & SPB_FLAG_FORCE_SPLIT);
+  const bool split = cfg.evaluator == SPB_EVAL_NET || (cfg.flags & SPB_FLAG_FORCE_SPLIT) || T.K > 1;
   if (cfg.evaluator == SPB_EVAL_NET && !evaluator.loaded()) { set_error("no weights loaded: call spb_load_weights first"); return SPB_ERR_STATE; }
   SPB_CUDA(cudaEventRecord(ev0, stream));
   last_eval_launches = 0;
@@ -648,6 +765,29 @@ int32_t spb_engine::search_t(uint32_t num_searches) {
     else k_search_fused<G, SPB_EVAL_UNIFORM><<<blocks, THREADS, 0, stream>>>(T, num_searches);
     SPB_CHECK_LAUNCH();
     ++launches;
+  } else if (T.K > 1) {
+    // EXTENSION: K leaves per tree per step with virtual loss (see k_tree_step_multi).
+    const uint32_t K = T.K, steps = (num_searches + K - 1) / K;
+    SPB_CUDA(cudaMemsetAsync(T.eval_count, 0, 8, stream));
+    k_tree_step_multi<G><<<blocks, THREADS, 0, stream>>>(T, 0, std::min(K, num_searches), 0u);
+    SPB_CHECK_LAUNCH();
+    ++launches;
+    for (uint32_t j = 0; j < steps; ++j) {
+      const bool last = (j == steps - 1);
+      if (last) {
+        SPB_CUDA(cudaMemcpyAsync(&T.eval_count[2], &T.eval_count[j & 1u], 4, cudaMemcpyDeviceToDevice, stream));
+        last_eval_parity = 2;
+      }
+      int32_t rc = launch_eval_step<G>(j);
+      if (rc != SPB_OK) return rc;
+      SPB_CHECK_LAUNCH();
+      ++last_eval_launches;
+      const uint32_t done_after = std::min(num_searches, (j + 1) * K);
+      const uint32_t k_next = last ? 0u : std::min(K, num_searches - done_after);
+      k_tree_step_multi<G><<<blocks, THREADS, 0, stream>>>(T, 1, k_next, j + 1);
+      SPB_CHECK_LAUNCH();
+      ++launches;
+    }
   } else {
     // step j: select writes eval_count[j&1]; the kernel also zeroes eval_count[(j+1)&1].
     SPB_CUDA(cudaMemsetAsync(T.eval_count, 0, 8, stream));
@@ -740,7 +880,7 @@ int32_t spb_create(const spb_config* cfg, spb_engine** out) {
   if (cfg->abi_version != SPB_ABI_VERSION) { g_create_error = "abi_version mismatch"; return SPB_ERR_ARG; }
   if (cfg->game != SPB_GAME_CONNECT4 && cfg->game != SPB_GAME_TICTACTOE) { g_create_error = "unknown game"; return SPB_ERR_ARG; }
   if (cfg->num_games == 0 || cfg->num_games > (1u << 22)) { g_create_error = "num_games out of range"; return SPB_ERR_ARG; }
-  if (cfg->leaves_per_tree != 1) { g_create_error = "leaves_per_tree must be 1 (virtual-loss multi-leaf search is not in this build)"; return SPB_ERR_ARG; }
+  if (cfg->leaves_per_tree < 1 || cfg->leaves_per_tree > 16) { g_create_error = "leaves_per_tree must be in 1..16"; return SPB_ERR_ARG; }
   if (cfg->evaluator < SPB_EVAL_NET || cfg->evaluator > SPB_EVAL_UNIFORM) { g_create_error = "unknown evaluator"; return SPB_ERR_ARG; }
   if (!(cfg->c == cfg->c)) { g_create_error = "c is NaN"; return SPB_ERR_ARG; }
   spb_engine* e = new (std::nothrow) spb_engine();
