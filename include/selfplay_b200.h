@@ -96,6 +96,8 @@ typedef struct spb_config {
 
 #define SPB_FLAG_NO_GRAPH   1u   /* launch kernels directly instead of through a CUDA graph */
 #define SPB_FLAG_EVAL_SIMT  2u   /* use the CUDA-core evaluator kernel instead of tcgen05 (debug / cross-check) */
+#define SPB_FLAG_EVAL_DX    8u   /* experimental tcgen05 evaluator variant: the three kx taps of a kernel row share one A read (N = 192)
+                                    and the dx shift moves into the epilogue as warp shuffles */
 #define SPB_FLAG_FORCE_SPLIT 4u  /* run DetEval / uniform through the lock-step select -> evaluate -> expand pipeline
                                     of the network evaluator instead of the fused single-kernel search */
 

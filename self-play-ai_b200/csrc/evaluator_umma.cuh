@@ -16,4 +16,11 @@ cudaError_t launch(const Evaluator::DevNet& net, int game, const PState* states,
                    cudaStream_t stream);
 
 }  // namespace umma
+
+namespace umma_v1 {   // first version (one MMA group per tap, N = 64); cross-check only
+void pack_weights(const HostNet& net, std::vector<uint8_t>* out);
+cudaError_t launch(const Evaluator::DevNet& net, int game, const PState* states, const uint32_t* list,
+                   const uint32_t* count_dev, uint32_t max_n, float* out, int stride, float* logits_out,
+                   cudaStream_t stream);
+}  // namespace umma_v1
 }  // namespace spb

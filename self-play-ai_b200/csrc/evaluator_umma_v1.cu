@@ -1,5 +1,5 @@
-// evaluator_umma.cu — EXPERIMENTAL dx-sharing variant of the fused policy/value network on tcgen05 (SPB_FLAG_EVAL_DX).
-// The default kernel is evaluator_umma_v1.cu; this one is correct (same parity tests) but not yet faster, see DESIGN.md §4.2.
+// evaluator_umma_v1.cu — the fused policy/value network on tcgen05 tensor cores (sm_100a): one MMA group per 3x3 tap (N = 64).
+// This is the DEFAULT evaluator kernel.  evaluator_umma.cu holds the experimental dx-sharing variant (SPB_FLAG_EVAL_DX).
 //
 // Replaces Net::forward + softmax of the reference (ref: src/model/connect_four.rs:75-81,
 // src/model/tictactoe.rs:75-81, src/model/mod.rs:62-63; layers model/mod.rs:152-184,
@@ -9,28 +9,23 @@
 // them with the activations resident in shared memory:
 //
 //   positions  a board is laid out as RP rows of W8 cells (Connect4: 7 x 8, one zero pad column and one
-//              zero pad row), boards back to back: row index m = board*BS + r*W8 + c.  A 3x3 tap (ky,kx) is
-//              the constant row offset (ky-1)*W8 + (kx-1); the zero pad cells give the conv's zero padding.
-//   A operand  activations, bf16, K-major, NO swizzle: [8 channel-chunks][Q rows][8 channels]: an 8-row core
-//              matrix is contiguous at ANY row offset, so a row shift is just a different start address in the
-//              shared-memory descriptor (checked on hardware: tools/umma_probe.cu).
-//   dx sharing In SS mode the A fetch (128 rows x 32 B) costs ~45 cycles per MMA whatever N is (probe), so one
-//              A read must feed as many output columns as possible: the three kx taps of a kernel row share
-//              the SAME shifted A and are concatenated along N (N = 3*64 = 192, tensor-bound at 96 cycles):
-//                  E_kx[q] = sum_ky A[q + (ky-1)*W8] * W[ky][kx]        (3 MMA groups per layer instead of 9)
-//                  out[p]  = E_0[p-1] + E_1[p] + E_2[p+1]               (epilogue: +-1-lane warp shuffles)
-//              Rows 32k-1 are pad cells (W8 divides 32), where E is identically 0 and the output is forced to
-//              0, so no value ever crosses a warp or tile boundary.
-//   B operand  weights of one (ky, k-step): bf16 [2 chunks][3N rows][8], 6 KB, streamed into a 12-slot ring by
-//              cp.async.bulk (TMA, 1-D) from an L2-resident image; BatchNorm is folded in on the host.
-//   D          fp32 accumulators in TMEM: two sets of 192 columns, ping-ponged per tile.
-//   epilogue   16 warps (four per TMEM lane quadrant, 16 channels each): tcgen05.ld of the three kx blocks,
-//              release the accumulator set, shuffle-sum, +bias (+skip), ReLU, bf16, st.shared into the other
-//              activation buffer (pad rows forced to zero) = next layer's A operand.  Head layer: the two
+//              zero pad row), boards back to back: row index m = board*BS + r*W8 + c.  With this layout a
+//              3x3 tap (dy,dx) is a constant row offset dy*W8+dx, and the zero pad cells give the conv's
+//              zero padding for free.  NB boards = 4 tiles of 128 rows.
+//   A operand  activations, bf16, K-major, NO swizzle: [8 channel-chunks][Q rows][8 channels] so that a core
+//              matrix (8 rows x 16 B) is contiguous at ANY row offset -> the tap shift is just a different
+//              start address in the shared-memory descriptor (checked on hardware: tools/umma_probe.cu).
+//   B operand  weights of one tap, bf16 [8 chunks][N out-channels][8], streamed per layer into a 9-slot ring
+//              by cp.async.bulk (TMA, 1-D) from an L2-resident image; BatchNorm is folded in on the host.
+//   D          fp32 accumulators in TMEM, one 64-column block per tile (4 x 64 = 256 columns).
+//   MMA        tcgen05.mma.cta_group::1.kind::f16, M=128, N=64 (48 for the fused policy+value head conv),
+//              K=16; 9 taps x 4 k-steps accumulate one tile of one layer.
+//   epilogue   8 warps (two per TMEM lane quadrant, 32 channels each): tcgen05.ld -> +bias (+skip) -> ReLU -> bf16 -> st.shared into the other activation
+//              buffer (pad rows forced to zero), which is the next layer's A operand.  Head layer: the two
 //              Linear layers, softmax and tanh are computed from the accumulators.
 //
-// Warp roles: warp 0 = weight producer (one lane), warp 1 = TMEM allocator + MMA issuer (one elected lane,
-// warp-uniform control flow), warps 2..17 = epilogue.  Hand-offs are mbarriers only.
+// Warp roles: warp 0 = weight producer (one lane), warp 1 = TMEM allocator + MMA issuer (one lane),
+// warps 2..9 = epilogue (TMEM lane quadrant = warp & 3, channel half = (warp-2)/4).  Hand-offs are mbarriers only.
 #include <cuda_bf16.h>
 
 #include <cstring>
@@ -38,19 +33,19 @@
 #include "evaluator_umma.cuh"
 
 namespace spb {
-namespace umma {
+namespace umma_v1 {
 
 // ---------------------------------------------------------------------------------------------------
 // geometry
 // ---------------------------------------------------------------------------------------------------
 template <class G>
 struct Geo {
-  static constexpr int W8 = (G::COLS == 7) ? 8 : 4;          // padded row width (divides 32)
+  static constexpr int W8 = (G::COLS == 7) ? 8 : 4;          // padded row width
   static constexpr int RP = G::ROWS + 1;                     // rows incl. the shared zero pad row
   static constexpr int BS = W8 * RP;                         // rows per board (56 / 16)
   static constexpr int NT = 4;                               // tiles per batch
   static constexpr int NB = (NT * 128) / BS;                 // boards per batch (9 / 32)
-  static constexpr int LEAD = 16;                            // zero rows in front (a kernel row reaches back W8)
+  static constexpr int LEAD = 16;                            // zero rows in front (taps reach back W8+1)
   static constexpr int Q = LEAD + NT * 128 + 16;             // rows of an activation buffer
   static constexpr int P = G::ROWS * G::COLS;
   static constexpr int APAD = (G::A <= 8) ? 8 : 16;          // policy FC weights per (pos, channel), bf16
@@ -58,16 +53,16 @@ struct Geo {
 
 constexpr int N_LAYERS = 10;          // stem, 8 residual convs, fused head conv
 constexpr int HEAD_N = 48;            // 32 policy + 3 value + 13 zero output channels
-constexpr int SLOT_BYTES = 6144;      // one (ky, k-step) block of a 64->64 layer: 2 chunks x 192 rows x 16 B
-constexpr int N_SLOTS = 12;           // 3 kernel rows x 4 k-steps = one whole layer
+constexpr int SLOT_BYTES = 8192;      // one tap of a 64->64 layer
+constexpr int N_SLOTS = 9;
 
 __host__ __device__ constexpr int layer_n(int l) { return l == 9 ? HEAD_N : 64; }
-__host__ __device__ constexpr int layer_ksteps(int l) { return l == 0 ? 1 : 4; }
-__host__ __device__ constexpr int layer_block_bytes(int l) { return 2 * 3 * layer_n(l) * 16; }
+__host__ __device__ constexpr int layer_kchunks(int l) { return l == 0 ? 2 : 8; }
+__host__ __device__ constexpr int layer_tap_bytes(int l) { return layer_kchunks(l) * layer_n(l) * 16; }
 __host__ __device__ constexpr size_t layer_offset(int l) {
-  return l == 0 ? 0 : (size_t)3 * SLOT_BYTES + (size_t)(l - 1) * 12 * SLOT_BYTES;
+  return l == 0 ? 0 : (size_t)9 * 2048 + (size_t)(l - 1) * 9 * SLOT_BYTES;
 }
-constexpr size_t OFF_BIAS = (size_t)3 * SLOT_BYTES + (size_t)8 * 12 * SLOT_BYTES + (size_t)12 * 4608;
+constexpr size_t OFF_BIAS = (size_t)9 * 2048 + (size_t)8 * 9 * SLOT_BYTES + (size_t)9 * 6144;   // 663,552
 constexpr size_t OFF_WP = OFF_BIAS + (size_t)N_LAYERS * 64 * 4;
 template <class G> __host__ __device__ constexpr size_t off_wv() { return OFF_WP + (size_t)Geo<G>::P * 32 * Geo<G>::APAD * 2; }
 template <class G> __host__ __device__ constexpr size_t off_fcb() { return off_wv<G>() + (size_t)Geo<G>::P * 4 * 4; }
@@ -90,27 +85,23 @@ static void pack_t(const HostNet& net, std::vector<uint8_t>* out) {
   out->assign(image_bytes<G>(), 0);
   uint8_t* img = out->data();
   for (int l = 0; l < N_LAYERS; ++l) {
-    const int N = layer_n(l), KS = layer_ksteps(l);
-    for (int ky = 0; ky < 3; ++ky)
-      for (int kk = 0; kk < KS; ++kk) {
-        uint16_t* blk = reinterpret_cast<uint16_t*>(img + layer_offset(l) + (size_t)(ky * KS + kk) * layer_block_bytes(l));
-        for (int kx = 0; kx < 3; ++kx)
-          for (int n = 0; n < N; ++n) {
-            const HostNet::Conv* cv;
-            int oc;
-            if (l < 9) { cv = &net.conv[l]; oc = n; }
-            else if (n < NET_POLICY_CH) { cv = &net.conv[9]; oc = n; }
-            else if (n < NET_POLICY_CH + NET_VALUE_CH) { cv = &net.conv[10]; oc = n - NET_POLICY_CH; }
-            else continue;
-            for (int j = 0; j < 2; ++j)
-              for (int e = 0; e < 8; ++e) {
-                const int k = kk * 16 + j * 8 + e;                       // input channel
-                if (k >= cv->ic) continue;
-                const float w = cv->w[((size_t)oc * cv->ic + k) * 9 + ky * 3 + kx];   // [OC][IC][ky][kx]
-                blk[((size_t)j * 3 * N + kx * N + n) * 8 + e] = f2bf(w);
-              }
-          }
+    const int N = layer_n(l), KC = layer_kchunks(l);
+    for (int tap = 0; tap < 9; ++tap) {
+      uint16_t* blk = reinterpret_cast<uint16_t*>(img + layer_offset(l) + (size_t)tap * layer_tap_bytes(l));
+      for (int n = 0; n < N; ++n) {
+        const HostNet::Conv* cv;
+        int oc;
+        if (l < 9) { cv = &net.conv[l]; oc = n; }
+        else if (n < NET_POLICY_CH) { cv = &net.conv[9]; oc = n; }
+        else if (n < NET_POLICY_CH + NET_VALUE_CH) { cv = &net.conv[10]; oc = n - NET_POLICY_CH; }
+        else continue;
+        for (int k = 0; k < KC * 8; ++k) {
+          if (k >= cv->ic) break;
+          float w = cv->w[((size_t)oc * cv->ic + k) * 9 + tap];   // [OC][IC][ky][kx], tap = ky*3+kx
+          blk[((size_t)(k / 8) * N + n) * 8 + (k % 8)] = f2bf(w);
+        }
       }
+    }
   }
   float* bias = reinterpret_cast<float*>(img + OFF_BIAS);
   for (int l = 0; l < 9; ++l)
@@ -149,6 +140,15 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
                  : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
   } while (!ok);
 }
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {   // for the producer: don't hog issue slots
+  uint32_t ok;
+  for (;;) {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (ok) break;
+    __nanosleep(200);
+  }
+}
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory"); }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
@@ -174,35 +174,22 @@ __device__ __forceinline__ bool elect_one() {
   asm volatile("{\n.reg .pred P1;\nelect.sync _|P1, 0xffffffff;\nselp.u32 %0, 1, 0, P1;\n}" : "=r"(pred));
   return pred != 0;
 }
-constexpr int EPI_THREADS = 512;
-constexpr int EPI_WARPS = EPI_THREADS / 32;   // mbarrier arrivals are per warp (one lane after __syncwarp): 32x fewer shared-memory atomics
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
-// Warp-level hand-offs: every lane has done its part (stores + proxy fence, or TMEM loads + wait); one lane arrives.
-__device__ __forceinline__ void warp_arrive(uint32_t bar, int lane) {
-  __syncwarp();
-  if (lane == 0) mbar_arrive(bar);
-}
-// One lane polls the mbarrier, the warp then synchronises on it.
-__device__ __forceinline__ void warp_wait(uint32_t bar, uint32_t parity, int lane) {
-  if (lane == 0) mbar_wait(bar, parity);
-  __syncwarp();
-}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
                  "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
                : "r"(taddr));
 }
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* r) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t* r) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr));
-}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// K-major, SWIZZLE_NONE shared-memory matrix descriptor: LBO = byte stride between the two 8-element K
+// chunks of one MMA, SBO = byte stride between 8-row groups (verified by tools/umma_probe.cu).
+__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((addr >> 4) & 0x3FFFu) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) |
+         ((uint64_t)1 << 46);
+}
 // kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major, M = 128.
 __host__ __device__ constexpr uint32_t make_idesc(int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -215,56 +202,40 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 __device__ __forceinline__ float bf_lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
 
-// out[p] = E_0[p-1] + E_1[p] + E_2[p+1] for one channel: lane p-1 holds E_0[p-1], lane p+1 holds E_2[p+1].
-// Rotating shuffles need no edge handling: lane 0 receives lane 31's E_0, and lane 31 is a pad-column cell
-// (W8 divides 32) where E is exactly 0 because every input it sees is a zero pad cell; lane 31 receives lane 0's
-// E_2, but lane 31's own output is a pad cell and is forced to zero anyway.
-__device__ __forceinline__ float dx_sum(uint32_t em, uint32_t e0, uint32_t ep, int lane) {
-  const float l = __shfl_sync(0xffffffffu, __uint_as_float(em), (lane + 31) & 31);
-  const float r = __shfl_sync(0xffffffffu, __uint_as_float(ep), (lane + 1) & 31);
-  return (__uint_as_float(e0) + l) + r;
-}
-// ReLU on two packed bf16 values (identical to rounding the ReLU of the fp32 values).
-__device__ __forceinline__ uint32_t relu_bf16x2(uint32_t v) {
-  __nv_bfloat162 x = *reinterpret_cast<__nv_bfloat162*>(&v);
-  x = __hmax2(x, __floats2bfloat162_rn(0.0f, 0.0f));
-  return *reinterpret_cast<uint32_t*>(&x);
-}
-
-// Issues the 3 kernel rows x KSTEPS MMAs of one (layer, tile).  A descriptor low word = a_lo_tile + row shift +
-// k-step * 2Q (two K chunks further); B = ring slot (ky, kk).  Descriptor high words are constants
-// (SBO = 128 B, version 1).  K-major SWIZZLE_NONE: LBO = byte stride between the two K chunks of one MMA.
+// Issues the 9 taps x KSTEPS MMAs of one (layer, tile).  Descriptor low words: A = a_lo_tile + tap shift +
+// kk * 2Q (two K chunks further), B = slot base + tap * slot stride + kk * 2N; high words are constants.
 template <int W8, int Q, int KSTEPS, int N>
-__device__ __forceinline__ void issue_tile(bool issuer, uint32_t a_lo_tile, uint32_t b_lo_base, uint32_t d_tmem,
-                                           bool first_tile, bool last_tile, uint32_t w_par_mask, uint32_t bar_base,
+__device__ __forceinline__ void issue_tile(bool issuer, uint32_t a_lo_tile, uint32_t b_lo_base, uint32_t slot_stride16,
+                                           uint32_t d_tmem, bool first_tile, bool last_tile, uint32_t w_par, uint32_t bar_base,
                                            unsigned long long& prof_wfull) {
-  constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);
-  constexpr uint32_t IDESC = make_idesc(3 * N);
+  constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);          // SBO = 128 B, descriptor version 1
+  constexpr uint32_t IDESC = make_idesc(N);
+  (void)slot_stride16;
 #pragma unroll
-  for (int ky = 0; ky < 3; ++ky) {
+  for (int tap = 0; tap < 9; ++tap) {
+    if (first_tile) {                                                                            // w_full[tap]
+#ifdef SPB_PROFILE
+      const unsigned long long t0 = clock64();
+#endif
+      mbar_wait(bar_base + (uint32_t)tap * 8u, w_par);
+#ifdef SPB_PROFILE
+      prof_wfull += clock64() - t0;
+#endif
+      tc_fence_after();
+    }
+    const int shift = (tap / 3 - 1) * W8 + (tap % 3 - 1);
+    if (issuer) {
 #pragma unroll
-    for (int kk = 0; kk < KSTEPS; ++kk) {
-      const int slot = ky * 4 + kk;
-      if (first_tile) {                                                                          // w_full[slot]
-#ifdef SPB_PROFILE
-        const unsigned long long t0 = clock64();
-#endif
-        mbar_wait(bar_base + (uint32_t)slot * 8u, (w_par_mask >> slot) & 1u);
-#ifdef SPB_PROFILE
-        prof_wfull += clock64() - t0;
-#endif
-        tc_fence_after();
-      }
-      if (issuer) {
-        const uint32_t a_lo = a_lo_tile + (uint32_t)((ky - 1) * W8 + kk * 2 * Q);
-        const uint32_t b_lo = (b_lo_base + (uint32_t)slot * (SLOT_BYTES >> 4)) | ((uint32_t)(3 * N) << 16);
+      for (int kk = 0; kk < KSTEPS; ++kk) {
+        const uint32_t a_lo = a_lo_tile + (uint32_t)(shift + kk * 2 * Q);
+        const uint32_t b_lo = (b_lo_base + (uint32_t)tap * (SLOT_BYTES >> 4) + (uint32_t)(kk * 2 * N)) | ((uint32_t)N << 16);
         const uint64_t ad = ((uint64_t)DESC_HI << 32) | a_lo;
         const uint64_t bd = ((uint64_t)DESC_HI << 32) | b_lo;
-        umma_f16(d_tmem, ad, bd, IDESC, (ky | kk) != 0);
-        if (last_tile) umma_commit(bar_base + (uint32_t)(N_SLOTS + slot) * 8u);                  // w_empty[slot]
+        umma_f16(d_tmem, ad, bd, IDESC, (tap | kk) != 0);
       }
-      __syncwarp();
+      if (last_tile) umma_commit(bar_base + (uint32_t)(N_SLOTS + tap) * 8u);                    // w_empty[tap]
     }
+    __syncwarp();
   }
 }
 
@@ -277,29 +248,28 @@ struct Smem {
   static constexpr int ACT_BYTES = 8 * Ge::Q * 16;                 // 69,632
   static constexpr int OFF_ACT0 = 0;
   static constexpr int OFF_ACT1 = ACT_BYTES;
-  static constexpr int OFF_W = 2 * ACT_BYTES;                      // 12 x 6 KB weight ring
+  static constexpr int OFF_W = 2 * ACT_BYTES;                      // 9 x 8 KB weight ring
   static constexpr int OFF_BIAS = OFF_W + N_SLOTS * SLOT_BYTES;    // 10 x 64 f32
-  static constexpr int OFF_LOGITS = OFF_BIAS + N_LAYERS * 64 * 4;  // [NB][16] f32
+  static constexpr int OFF_LOGITS = OFF_BIAS + N_LAYERS * 64 * 4;  // [NB][16] f32 (policy partial sums, value at [15])
   static constexpr int OFF_PART = OFF_LOGITS + Ge::NB * 16 * 4;    // [NB][ROWS][16] f32 row partials of the Linear layers
   static constexpr int OFF_STATES = OFF_PART + Ge::NB * G::ROWS * 16 * 4;   // [2][NB] PState
-  static constexpr int OFF_SLOTS = OFF_STATES + 2 * Ge::NB * 16;   // [2][NB] u32
+  static constexpr int OFF_SLOTS = OFF_STATES + 2 * Ge::NB * 16;   // [2][NB] u32 (states/slots ping-pong per batch)
   static constexpr int OFF_BARS = (OFF_SLOTS + 2 * Ge::NB * 4 + 15) & ~15;
-  // barriers: w_full[12], w_empty[12], acc_full[2], acc_empty[2], act_ready[4], stage_ready[4]
-  static constexpr int N_BARS = 2 * N_SLOTS + 4 + 2 * Ge::NT;
-  static constexpr int OFF_TMEM = OFF_BARS + N_BARS * 8;
+  // barriers: w_full[9], w_empty[9], acc_full[4], act_ready[4], stage_ready[4], acc_full of odd batches [4]
+  static constexpr int OFF_TMEM = OFF_BARS + (2 * N_SLOTS + 4 * Ge::NT) * 8;
   static constexpr int TOTAL = OFF_TMEM + 16;
 };
-static_assert(Smem<Connect4>::TOTAL <= 232448 && Smem<TicTacToe>::TOTAL <= 232448, "shared memory plan exceeds 227 KB");
 
-constexpr int THREADS = 64 + EPI_THREADS;     // producer warp, MMA warp, 16 epilogue warps
-constexpr int ACC_COLS = 192;                 // columns of one accumulator set (3 kx blocks x 64)
+static_assert(Smem<Connect4>::TOTAL <= 232448 && Smem<TicTacToe>::TOTAL <= 232448, "shared memory plan exceeds 227 KB");
+constexpr int THREADS = 320;     // producer warp, MMA warp, 8 epilogue warps
 
 #ifdef SPB_PROFILE
 // debug build only (make PROFILE=1): per-CTA cycle attribution
 __device__ unsigned long long g_eval_prof[160][8];
-__device__ int g_eval_debug = 0;   // bit0: skip epilogue math+stores, bit1: skip TMEM loads too
+__device__ unsigned long long g_eval_prof_layer[160][24];   // [cta][0..9] act waits per layer, [10..19] weight waits per layer
+__device__ int g_eval_debug = 0;   // bit0: epilogue skips tcgen05.ld, bit1: skips st.shared, bit2: skips skip-loads, bit3: no per-tap commits
 #define DBG(bit) (g_eval_debug & (1 << (bit)))
-#define PROF_DECL unsigned long long prof_t0 = 0, prof_acc0 = 0, prof_t1 = 0, prof_acc1 = 0, prof_acc2 = 0;
+#define PROF_DECL unsigned long long prof_t0 = 0, prof_acc0 = 0, prof_acc1 = 0, prof_acc2 = 0;
 #define PROF_BEGIN() (prof_t0 = clock64())
 #define PROF_END(acc) ((acc) += clock64() - prof_t0)
 #else
@@ -326,13 +296,15 @@ k_eval_umma(const uint8_t* __restrict__ image, const PState* __restrict__ states
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t s_base = smem_u32(smem);
   const uint32_t bar_base = s_base + Sm::OFF_BARS;
+  auto bar_w_full = [&](int s) { return bar_base + (uint32_t)s * 8u; };
   auto bar_w_empty = [&](int s) { return bar_base + (uint32_t)(N_SLOTS + s) * 8u; };
-  auto bar_acc_full = [&](uint32_t set) { return bar_base + (uint32_t)(2 * N_SLOTS + set) * 8u; };
-  auto bar_acc_empty = [&](uint32_t set) { return bar_base + (uint32_t)(2 * N_SLOTS + 2 + set) * 8u; };
-  auto bar_act_ready = [&](int t) { return bar_base + (uint32_t)(2 * N_SLOTS + 4 + t) * 8u; };
-  // The staged input of a batch has its own barrier: it may complete while act_ready's previous phase is still
-  // being consumed by the MMA warp (an mbarrier must never run two phases ahead of a waiter).
-  auto bar_stage_ready = [&](int t) { return bar_base + (uint32_t)(2 * N_SLOTS + 4 + Ge::NT + t) * 8u; };
+  // acc_full is per accumulator set (batch parity): the MMA warp may finish the next batch's stem tile before the
+  // epilogue has consumed this batch's head tile, and an mbarrier must never run two phases ahead of a waiter.
+  auto bar_acc_full = [&](uint32_t set, int t) { return bar_base + (uint32_t)(2 * N_SLOTS + (set ? 3 * Ge::NT : 0) + t) * 8u; };
+  auto bar_act_ready = [&](int t) { return bar_base + (uint32_t)(2 * N_SLOTS + Ge::NT + t) * 8u; };
+  // separate barrier for the staged input of a batch: it may complete while act_ready's previous phase is still
+  // being consumed by the MMA warp (an mbarrier must never run two phases ahead of a waiter)
+  auto bar_stage_ready = [&](int t) { return bar_base + (uint32_t)(2 * N_SLOTS + 2 * Ge::NT + t) * 8u; };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + Sm::OFF_TMEM);
 
   // ---- one-time setup -----------------------------------------------------------------------------
@@ -345,9 +317,8 @@ k_eval_umma(const uint8_t* __restrict__ image, const PState* __restrict__ states
     for (int i = tid; i < N_LAYERS * 64; i += THREADS) sb[i] = gb[i];
   }
   if (tid == 0) {
-    for (int s = 0; s < N_SLOTS; ++s) { mbar_init(bar_base + (uint32_t)s * 8u, 1); mbar_init(bar_w_empty(s), 1); }
-    for (uint32_t s = 0; s < 2; ++s) { mbar_init(bar_acc_full(s), 1); mbar_init(bar_acc_empty(s), EPI_WARPS); }
-    for (int t = 0; t < Ge::NT; ++t) { mbar_init(bar_act_ready(t), EPI_WARPS); mbar_init(bar_stage_ready(t), EPI_WARPS); }
+    for (int s = 0; s < N_SLOTS; ++s) { mbar_init(bar_w_full(s), 1); mbar_init(bar_w_empty(s), 1); }
+    for (int t = 0; t < Ge::NT; ++t) { mbar_init(bar_acc_full(0, t), 1); mbar_init(bar_acc_full(1, t), 1); mbar_init(bar_act_ready(t), 256); mbar_init(bar_stage_ready(t), 256); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
@@ -360,29 +331,26 @@ k_eval_umma(const uint8_t* __restrict__ image, const PState* __restrict__ states
   const uint32_t n_batches = (my_end - my_begin + Ge::NB - 1) / Ge::NB;
 
   if (warp == 0) {
-    // ===== weight producer: streams (layer, ky, k-step) blocks into the 12-slot ring ===================
+    // ===== weight producer: streams (layer, tap) blocks into the 9-slot ring ==========================
     if (lane == 0) {
-      uint32_t filled = 0, par = 0;                                // per slot: ever filled / parity of its next release
+      uint32_t use = 0;                                           // completed fills of every slot
       for (uint32_t b = 0; b < n_batches; ++b) {
         for (int l = 0; l < N_LAYERS; ++l) {
-          const int KS = layer_ksteps(l);
-          const uint32_t bytes = (uint32_t)layer_block_bytes(l);
+          const uint32_t bytes = (uint32_t)layer_tap_bytes(l);
           const uint8_t* src = image + layer_offset(l);
-          for (int ky = 0; ky < 3; ++ky)
-            for (int kk = 0; kk < KS; ++kk) {
-              const int s = ky * 4 + kk;
-              if ((filled >> s) & 1u) { mbar_wait(bar_w_empty(s), (par >> s) & 1u); par ^= 1u << s; }
-              filled |= 1u << s;
-              mbar_expect_tx(bar_base + (uint32_t)s * 8u, bytes);
-              bulk_g2s(s_base + Sm::OFF_W + (uint32_t)s * SLOT_BYTES, src + (size_t)(ky * KS + kk) * bytes, bytes, bar_base + (uint32_t)s * 8u);
-            }
+          for (int s = 0; s < N_SLOTS; ++s) {
+            if (use > 0) mbar_wait(bar_w_empty(s), (use - 1) & 1u);
+            mbar_expect_tx(bar_w_full(s), bytes);
+            bulk_g2s(s_base + Sm::OFF_W + (uint32_t)s * SLOT_BYTES, src + (size_t)s * bytes, bytes, bar_w_full(s));
+          }
+          ++use;
         }
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer ===============================================================================
     // The whole warp runs the (warp-uniform) control flow so that descriptors stay in uniform registers;
-    // one elected lane issues the tcgen05 instructions.
+    // one fixed lane issues the tcgen05 instructions.
     {
       PROF_DECL
 #ifdef SPB_PROFILE
@@ -391,10 +359,9 @@ k_eval_umma(const uint8_t* __restrict__ image, const PState* __restrict__ states
       unsigned long long prof_w = 0;
       const bool issuer = elect_one();
       const uint32_t b_lo_base = ((s_base + Sm::OFF_W) >> 4);
-      uint32_t w_par = 0;      // bit s: parity of the next fill of ring slot s
+      uint32_t use = 0;        // layer-uses of the weight ring so far
       uint32_t act_par = 0;    // bit t: parity of the next completion of act_ready[t]
       uint32_t stage_par = 0;  // same for stage_ready[t]
-      uint32_t tile_ctr = 0;   // tiles issued so far; accumulator set = tile_ctr & 1
       for (uint32_t b = 0; b < n_batches; ++b) {
         const uint32_t nb = min((uint32_t)Ge::NB, my_end - my_begin - b * Ge::NB);
         const int nt = (int)((nb * Ge::BS + 127) / 128);
@@ -403,42 +370,49 @@ k_eval_umma(const uint8_t* __restrict__ image, const PState* __restrict__ states
           const uint32_t a_lo_base = ((in_buf >> 4) + Ge::LEAD) | ((uint32_t)Ge::Q << 16);
           const uint32_t cur_par = (l == 0) ? stage_par : act_par;
           if (l == 0) stage_par ^= (1u << nt) - 1u; else act_par ^= (1u << nt) - 1u;
-          const uint32_t slots_used = (l == 0) ? 0x111u : 0xFFFu;
-          for (int t = 0; t < nt; ++t, ++tile_ctr) {
+          for (int t = 0; t < nt; ++t) {
             const int wt = min(t + 1, nt - 1);                   // epilogue runs tiles in order: tile wt done => 0..wt done
-            const uint32_t set = tile_ctr & 1u;
             PROF_BEGIN();
             mbar_wait(l == 0 ? bar_stage_ready(wt) : bar_act_ready(wt), (cur_par >> wt) & 1u);
-            if (tile_ctr >= 2) mbar_wait(bar_acc_empty(set), ((tile_ctr >> 1) - 1u) & 1u);   // set drained by the epilogue
             PROF_END(prof_acc0);
+#ifdef SPB_PROFILE
+            if (lane == 0) g_eval_prof_layer[blockIdx.x][l] += clock64() - prof_t0;
+            const unsigned long long w_before = prof_w;
+#endif
             tc_fence_after();
             const uint32_t a_lo_tile = a_lo_base + (uint32_t)t * 128u;
-            const uint32_t d_tmem = tmem_base + set * (uint32_t)ACC_COLS;
+            const uint32_t d_tmem = tmem_base + (b & 1u) * 256u + (uint32_t)t * 64u;   // accumulators ping-pong per batch
             const bool first = (t == 0), last = (t == nt - 1);
-            if (l == 0)      issue_tile<Ge::W8, Ge::Q, 1, 64>(issuer, a_lo_tile, b_lo_base, d_tmem, first, last, w_par, bar_base, prof_w);
-            else if (l < 9)  issue_tile<Ge::W8, Ge::Q, 4, 64>(issuer, a_lo_tile, b_lo_base, d_tmem, first, last, w_par, bar_base, prof_w);
-            else             issue_tile<Ge::W8, Ge::Q, 4, HEAD_N>(issuer, a_lo_tile, b_lo_base, d_tmem, first, last, w_par, bar_base, prof_w);
-            if (issuer) umma_commit(bar_acc_full(set));
+            if (l == 0)
+              issue_tile<Ge::W8, Ge::Q, 1, 64>(issuer, a_lo_tile, b_lo_base, 2048 >> 4, d_tmem, first, last, use & 1u, bar_base, prof_w);
+            else if (l < 9)
+              issue_tile<Ge::W8, Ge::Q, 4, 64>(issuer, a_lo_tile, b_lo_base, SLOT_BYTES >> 4, d_tmem, first, last, use & 1u, bar_base, prof_w);
+            else
+              issue_tile<Ge::W8, Ge::Q, 4, HEAD_N>(issuer, a_lo_tile, b_lo_base, SLOT_BYTES >> 4, d_tmem, first, last, use & 1u, bar_base, prof_w);
+#ifdef SPB_PROFILE
+            if (lane == 0) g_eval_prof_layer[blockIdx.x][10 + l] += prof_w - w_before;
+#endif
+            if (issuer) umma_commit(bar_acc_full(b & 1u, t));
             __syncwarp();
           }
-          w_par ^= slots_used;
+          ++use;
         }
       }
 #ifdef SPB_PROFILE
       if (lane == 0) {
         g_eval_prof[blockIdx.x][0] = clock64() - prof_start;   // MMA warp total
-        g_eval_prof[blockIdx.x][1] = prof_acc0;                // waiting for activations / accumulator release
+        g_eval_prof[blockIdx.x][1] = prof_acc0;                // waiting for activations (epilogue)
         g_eval_prof[blockIdx.x][2] = n_batches;
-        g_eval_prof[blockIdx.x][5] = prof_w;                   // waiting for weights (TMA ring)
+        g_eval_prof[blockIdx.x][5] = prof_w;                    // waiting for weights (TMA ring)
       }
 #endif
     }
   } else {
-    // ===== epilogue warps (16 warps, 512 threads): encode, per-layer epilogues, heads ===================
-    // Four warps share a TMEM lane quadrant (a tile row) and split the 64 output channels in groups of 16.
-    const int et = tid - 64;                                       // 0..511
+    // ===== epilogue warps (8 warps, 256 threads): encode, per-layer epilogues, heads ====================
+    // Two warps share a TMEM lane quadrant (a tile row) and split the 64 output channels in halves.
+    const int et = tid - 64;                                       // 0..255
     const int quad = warp & 3;                                     // TMEM lanes [32*quad, 32*quad+32)
-    const int cg = (warp - 2) >> 2;                                // channels [16*cg, 16*cg+16)
+    const int half = (warp - 2) >> 2;                              // channels [32*half, 32*half+32)
     const int row_in_tile = quad * 32 + lane;
     const float* s_bias = reinterpret_cast<const float*>(smem + Sm::OFF_BIAS);
     float* s_logits = reinterpret_cast<float*>(smem + Sm::OFF_LOGITS);
@@ -448,8 +422,8 @@ k_eval_umma(const uint8_t* __restrict__ image, const PState* __restrict__ states
     const uint16_t* g_wp = reinterpret_cast<const uint16_t*>(image + OFF_WP);
     const float* g_wv = reinterpret_cast<const float*>(image + off_wv<G>());
     const float* g_fcb = reinterpret_cast<const float*>(image + off_fcb<G>());
-    constexpr int PCH = (G::A + 1 + 3) / 4;                        // 16-B chunks of head partial sums per channel half
-    uint32_t tile_ctr = 0;                                         // same sequence as the MMA warp
+    constexpr int PCH = (G::A + 1 + 3) / 4;                        // 16-B chunks of head partial sums per half
+    uint32_t acc_par[2] = {0, 0};                                  // [set] bit t: parity of the next completion of acc_full[set][t]
     PROF_DECL
 #ifdef SPB_PROFILE
     const unsigned long long prof_start = clock64();
@@ -471,20 +445,18 @@ k_eval_umma(const uint8_t* __restrict__ image, const PState* __restrict__ states
       }
       epi_bar_sync();
       for (int t = 0; t < nt; ++t) {
-        if (cg < 2) {
-          const int m = t * 128 + row_in_tile;
-          const int bi = m / Ge::BS, rem = m % Ge::BS, r = rem / Ge::W8, c = rem % Ge::W8;
-          uint4 v0 = make_uint4(0, 0, 0, 0);
-          if (cg == 0 && (uint32_t)bi < nb && r < G::ROWS && c < G::COLS) {
-            const PState st = st_buf[bi];
-            const float e0 = G::encode_cell(st, 0, r, c), e1 = G::encode_cell(st, 1, r, c), e2 = G::encode_cell(st, 2, r, c);
-            v0.x = pack_bf16x2(e0, e1);
-            v0.y = pack_bf16x2(e2, 0.0f);
-          }
-          *reinterpret_cast<uint4*>(smem + Sm::OFF_ACT0 + (size_t)cg * Ge::Q * 16 + (size_t)(Ge::LEAD + m) * 16) = v0;
+        const int m = t * 128 + row_in_tile;
+        const int bi = m / Ge::BS, rem = m % Ge::BS, r = rem / Ge::W8, c = rem % Ge::W8;
+        uint4 v0 = make_uint4(0, 0, 0, 0);
+        if (half == 0 && (uint32_t)bi < nb && r < G::ROWS && c < G::COLS) {
+          const PState st = st_buf[bi];
+          const float e0 = G::encode_cell(st, 0, r, c), e1 = G::encode_cell(st, 1, r, c), e2 = G::encode_cell(st, 2, r, c);
+          v0.x = pack_bf16x2(e0, e1);
+          v0.y = pack_bf16x2(e2, 0.0f);
         }
+        *reinterpret_cast<uint4*>(smem + Sm::OFF_ACT0 + (size_t)half * Ge::Q * 16 + (size_t)(Ge::LEAD + m) * 16) = v0;
         fence_async_smem();
-        warp_arrive(bar_stage_ready(t), lane);
+        mbar_arrive(bar_stage_ready(t));
       }
     };
     stage_batch(0);
@@ -493,154 +465,121 @@ k_eval_umma(const uint8_t* __restrict__ image, const PState* __restrict__ states
       const uint32_t b0 = my_begin + b * Ge::NB;
       const uint32_t nb = min((uint32_t)Ge::NB, my_end - b0);
       const int nt = (int)((nb * Ge::BS + 127) / 128);
+      const uint32_t tmem_acc = tmem_base + (b & 1u) * 256u;
       const uint32_t* sl_cur = s_slots + (b & 1u) * Ge::NB;
       // ---- layers
       for (int l = 0; l < N_LAYERS; ++l) {
         const bool in0 = (l == 0 || (l >= 2 && (l & 1) == 0));
         uint8_t* dst_buf = smem + (in0 ? Sm::OFF_ACT1 : Sm::OFF_ACT0);
         const bool has_skip = (l >= 2 && (l & 1) == 0 && l <= 8);   // second conv of a residual block
+        const uint32_t cur_par = acc_par[b & 1u];
+        acc_par[b & 1u] ^= (1u << nt) - 1u;
         if (l < 9) {
-          float bias_r[16];                                         // this thread's 16 output channels
+          float bias_r[32];                                         // this thread's 32 output channels
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float4 bv = *reinterpret_cast<const float4*>(s_bias + l * 64 + cg * 16 + q * 4);
+          for (int q = 0; q < 8; ++q) {
+            const float4 bv = *reinterpret_cast<const float4*>(s_bias + l * 64 + half * 32 + q * 4);
             bias_r[4 * q] = bv.x; bias_r[4 * q + 1] = bv.y; bias_r[4 * q + 2] = bv.z; bias_r[4 * q + 3] = bv.w;
           }
-          for (int t = 0; t < nt; ++t, ++tile_ctr) {
-            const uint32_t set = tile_ctr & 1u;
+          for (int t = 0; t < nt; ++t) {
             const int m = t * 128 + row_in_tile;
             const int bi = m / Ge::BS, rem = m % Ge::BS, r = rem / Ge::W8, c = rem % Ge::W8;
             const bool valid = (uint32_t)bi < nb && r < G::ROWS && c < G::COLS;
-            uint8_t* drow = dst_buf + (size_t)(cg * 2) * Ge::Q * 16 + (size_t)(Ge::LEAD + m) * 16;   // chunk 2*cg
-            uint4 sk[2];
+            uint8_t* drow = dst_buf + (size_t)(half * 4) * Ge::Q * 16 + (size_t)(Ge::LEAD + m) * 16;   // chunk 4*half
+            uint4 sk[4];
             if (has_skip) {                                         // (x + f(x)).relu(), model/mod.rs:163
-              sk[0] = *reinterpret_cast<const uint4*>(drow);
-              sk[1] = *reinterpret_cast<const uint4*>(drow + (size_t)Ge::Q * 16);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) sk[j] = *reinterpret_cast<const uint4*>(drow + (size_t)j * Ge::Q * 16);
             }
             PROF_BEGIN();
-            warp_wait(bar_acc_full(set), (tile_ctr >> 1) & 1u, lane);
+            mbar_wait(bar_acc_full(b & 1u, t), (cur_par >> t) & 1u);
             PROF_END(prof_acc0);
-#ifdef SPB_PROFILE
-            prof_t1 = clock64();
-#endif
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + set * (uint32_t)ACC_COLS + (uint32_t)cg * 16u;
+            const uint32_t taddr = tmem_acc + ((uint32_t)(quad * 32) << 16) + (uint32_t)t * 64u + (uint32_t)half * 32u;
+            uint32_t a[32];
+            tmem_ld16(taddr, a);
+            tmem_ld16(taddr + 16, a + 16);
+            tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {                           // one 8-channel chunk = one 16-B store
-              uint32_t em[8], e0[8], ep[8];
-              if (!DBG(1)) {
-                tmem_ld8(taddr + j * 8, em);                        // kx = 0 block: E_0
-                tmem_ld8(taddr + 64 + j * 8, e0);                   // kx = 1 block: E_1
-                tmem_ld8(taddr + 128 + j * 8, ep);                  // kx = 2 block: E_2
-                tmem_ld_wait();
-              } else {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) em[e] = e0[e] = ep[e] = 0;
-              }
-              if (j == 1) {
-                tc_fence_before();
-                warp_arrive(bar_acc_empty(set), lane);              // accumulator set may be overwritten
-              }
-              if (DBG(0)) continue;
+            for (int j = 0; j < 4; ++j) {                           // one 8-channel chunk = one 16-B store
               float v[8];
 #pragma unroll
-              for (int e = 0; e < 8; ++e) v[e] = dx_sum(em[e], e0[e], ep[e], lane) + bias_r[j * 8 + e];
+              for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(a[j * 8 + e]) + bias_r[j * 8 + e];
               if (has_skip) {
                 v[0] += bf_lo(sk[j].x); v[1] += bf_hi(sk[j].x); v[2] += bf_lo(sk[j].y); v[3] += bf_hi(sk[j].y);
                 v[4] += bf_lo(sk[j].z); v[5] += bf_hi(sk[j].z); v[6] += bf_lo(sk[j].w); v[7] += bf_hi(sk[j].w);
               }
               uint4 o = make_uint4(0, 0, 0, 0);
               if (valid) {
-                o.x = relu_bf16x2(pack_bf16x2(v[0], v[1]));
-                o.y = relu_bf16x2(pack_bf16x2(v[2], v[3]));
-                o.z = relu_bf16x2(pack_bf16x2(v[4], v[5]));
-                o.w = relu_bf16x2(pack_bf16x2(v[6], v[7]));
+                o.x = pack_bf16x2(fmaxf(v[0], 0.f), fmaxf(v[1], 0.f));
+                o.y = pack_bf16x2(fmaxf(v[2], 0.f), fmaxf(v[3], 0.f));
+                o.z = pack_bf16x2(fmaxf(v[4], 0.f), fmaxf(v[5], 0.f));
+                o.w = pack_bf16x2(fmaxf(v[6], 0.f), fmaxf(v[7], 0.f));
               }
               *reinterpret_cast<uint4*>(drow + (size_t)j * Ge::Q * 16) = o;
             }
-            if (!DBG(2)) fence_async_smem();
-            warp_arrive(bar_act_ready(t), lane);
-#ifdef SPB_PROFILE
-            prof_acc1 += clock64() - prof_t1;
-#endif
+            fence_async_smem();
+            tc_fence_before();
+            mbar_arrive(bar_act_ready(t));
           }
         } else {
-#ifdef SPB_PROFILE
-          prof_t1 = clock64();
-#endif
           // The head conv's MMAs are in flight: stage the next batch now (buffer 0 is no longer read by this batch).
           if (b + 1 < n_batches) stage_batch(b + 1);
-          // ---- heads: policy conv channels 0..31 (16 per group, groups 0 and 1), value conv channels 32..34
-          // (group 1), then the per-position terms of the two Linear layers.  Groups 2 and 3 only release the set.
+          // ---- heads: policy conv channels 0..31 (16 per half), value conv channels 32..34 (half 1), then the
+          // per-position terms of the two Linear layers.
           const float* bias = s_bias + l * 64;
-          for (int t = 0; t < nt; ++t, ++tile_ctr) {
-            const uint32_t set = tile_ctr & 1u;
+          for (int t = 0; t < nt; ++t) {
             const int m = t * 128 + row_in_tile;
             const int bi = m / Ge::BS, rem = m % Ge::BS, r = rem / Ge::W8, c = rem % Ge::W8;
             const bool valid = (uint32_t)bi < nb && r < G::ROWS && c < G::COLS;
             const int pos = r * G::COLS + c;
+            // prefetch this position's policy-Linear weights (bf16 [pos][ch][APAD]) before waiting for the MMA
+            uint4 w[16 * (Ge::APAD / 8)];
+            if (valid) {
+              const uint4* wrow = reinterpret_cast<const uint4*>(g_wp + ((size_t)pos * NET_POLICY_CH + half * 16) * Ge::APAD);
+#pragma unroll
+              for (int i = 0; i < 16 * (Ge::APAD / 8); ++i) w[i] = __ldg(wrow + i);
+            }
             PROF_BEGIN();
-            warp_wait(bar_acc_full(set), (tile_ctr >> 1) & 1u, lane);
+            mbar_wait(bar_acc_full(b & 1u, t), (cur_par >> t) & 1u);
             PROF_END(prof_acc0);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + set * (uint32_t)ACC_COLS;
-            float pl[Ge::APAD + 4];
-#pragma unroll
-            for (int i = 0; i < Ge::APAD + 4; ++i) pl[i] = 0.0f;
-            float vl = 0.0f;
-            if (cg < 2) {
-              const uint4* wrow = reinterpret_cast<const uint4*>(g_wp + ((size_t)(valid ? pos : 0) * NET_POLICY_CH + cg * 16) * Ge::APAD);
-#pragma unroll
-              for (int h8 = 0; h8 < 2; ++h8) {                      // 8 policy channels at a time (register budget)
-                uint32_t em[8], e0[8], ep[8];
-                tmem_ld8(taddr + (uint32_t)(cg * 16 + h8 * 8), em);
-                tmem_ld8(taddr + HEAD_N + (uint32_t)(cg * 16 + h8 * 8), e0);
-                tmem_ld8(taddr + 2 * HEAD_N + (uint32_t)(cg * 16 + h8 * 8), ep);
-                tmem_ld_wait();
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                  const float act = fmaxf(dx_sum(em[e], e0[e], ep[e], lane) + bias[cg * 16 + h8 * 8 + e], 0.0f);
-                  if (valid) {
-#pragma unroll
-                    for (int q = 0; q < Ge::APAD / 8; ++q) {
-                      const uint4 wq = __ldg(wrow + (h8 * 8 + e) * (Ge::APAD / 8) + q);
-                      pl[q * 8 + 0] = fmaf(act, bf_lo(wq.x), pl[q * 8 + 0]); pl[q * 8 + 1] = fmaf(act, bf_hi(wq.x), pl[q * 8 + 1]);
-                      pl[q * 8 + 2] = fmaf(act, bf_lo(wq.y), pl[q * 8 + 2]); pl[q * 8 + 3] = fmaf(act, bf_hi(wq.y), pl[q * 8 + 3]);
-                      pl[q * 8 + 4] = fmaf(act, bf_lo(wq.z), pl[q * 8 + 4]); pl[q * 8 + 5] = fmaf(act, bf_hi(wq.z), pl[q * 8 + 5]);
-                      pl[q * 8 + 6] = fmaf(act, bf_lo(wq.w), pl[q * 8 + 6]); pl[q * 8 + 7] = fmaf(act, bf_hi(wq.w), pl[q * 8 + 7]);
-                    }
-                  }
-                }
-              }
-              if (cg == 1) {
-                uint32_t vm[4], v0[4], vp[4];
-                tmem_ld4(taddr + 32u, vm);
-                tmem_ld4(taddr + HEAD_N + 32u, v0);
-                tmem_ld4(taddr + 2 * HEAD_N + 32u, vp);
-                tmem_ld_wait();
-                const float a0 = fmaxf(dx_sum(vm[0], v0[0], vp[0], lane) + bias[32], 0.0f);
-                const float a1 = fmaxf(dx_sum(vm[1], v0[1], vp[1], lane) + bias[33], 0.0f);
-                const float a2 = fmaxf(dx_sum(vm[2], v0[2], vp[2], lane) + bias[34], 0.0f);
-                if (valid) {
-                  const float4 wv = __ldg(reinterpret_cast<const float4*>(g_wv) + pos);
-                  vl = fmaf(a0, wv.x, vl);
-                  vl = fmaf(a1, wv.y, vl);
-                  vl = fmaf(a2, wv.z, vl);
-                }
-              }
-            }
+            const uint32_t taddr = tmem_acc + ((uint32_t)(quad * 32) << 16) + (uint32_t)t * 64u;
+            uint32_t a[16], av[16];
+            tmem_ld16(taddr + (uint32_t)half * 16u, a);
+            if (half == 1) tmem_ld16(taddr + 32u, av);
+            tmem_ld_wait();
             tc_fence_before();
-            warp_arrive(bar_acc_empty(set), lane);
-            if (cg < 2) {
-              if (valid) {
-                pl[G::A] = vl;
-                // Per-position partial sums go to this row's own (now dead) cells of activation buffer 0: chunks
-                // 2+PCH*cg.. — pad rows stay zero, and every chunk >= 2 is rewritten by layer 1 before it is read again.
-                uint8_t* prow = smem + Sm::OFF_ACT0 + (size_t)(Ge::LEAD + m) * 16;
+            if (valid) {
+              float pl[Ge::APAD + 4];
 #pragma unroll
-                for (int q = 0; q < PCH; ++q)
-                  *reinterpret_cast<float4*>(prow + (size_t)(2 + PCH * cg + q) * Ge::Q * 16) = make_float4(pl[4 * q], pl[4 * q + 1], pl[4 * q + 2], pl[4 * q + 3]);
+              for (int i = 0; i < Ge::APAD + 4; ++i) pl[i] = 0.0f;
+#pragma unroll
+              for (int e = 0; e < 16; ++e) {
+                const float act = fmaxf(__uint_as_float(a[e]) + bias[half * 16 + e], 0.0f);
+#pragma unroll
+                for (int q = 0; q < Ge::APAD / 8; ++q) {
+                  const uint4 wq = w[e * (Ge::APAD / 8) + q];
+                  pl[q * 8 + 0] = fmaf(act, bf_lo(wq.x), pl[q * 8 + 0]); pl[q * 8 + 1] = fmaf(act, bf_hi(wq.x), pl[q * 8 + 1]);
+                  pl[q * 8 + 2] = fmaf(act, bf_lo(wq.y), pl[q * 8 + 2]); pl[q * 8 + 3] = fmaf(act, bf_hi(wq.y), pl[q * 8 + 3]);
+                  pl[q * 8 + 4] = fmaf(act, bf_lo(wq.z), pl[q * 8 + 4]); pl[q * 8 + 5] = fmaf(act, bf_hi(wq.z), pl[q * 8 + 5]);
+                  pl[q * 8 + 6] = fmaf(act, bf_lo(wq.w), pl[q * 8 + 6]); pl[q * 8 + 7] = fmaf(act, bf_hi(wq.w), pl[q * 8 + 7]);
+                }
               }
+              float vl = 0.0f;
+              if (half == 1) {
+                const float4 wv = __ldg(reinterpret_cast<const float4*>(g_wv) + pos);
+                vl = fmaf(fmaxf(__uint_as_float(av[0]) + bias[32], 0.0f), wv.x, vl);
+                vl = fmaf(fmaxf(__uint_as_float(av[1]) + bias[33], 0.0f), wv.y, vl);
+                vl = fmaf(fmaxf(__uint_as_float(av[2]) + bias[34], 0.0f), wv.z, vl);
+              }
+              pl[G::A] = vl;
+              // Per-position partial sums go to this row's own (now dead) cells of activation buffer 0: chunks
+              // 2+PCH*half.. — pad rows stay zero, and every chunk >= 2 is rewritten by layer 1 before it is read again.
+              uint8_t* prow = smem + Sm::OFF_ACT0 + (size_t)(Ge::LEAD + m) * 16;
+#pragma unroll
+              for (int q = 0; q < PCH; ++q)
+                *reinterpret_cast<float4*>(prow + (size_t)(2 + PCH * half + q) * Ge::Q * 16) = make_float4(pl[4 * q], pl[4 * q + 1], pl[4 * q + 2], pl[4 * q + 3]);
             }
           }
         }
@@ -650,7 +589,7 @@ k_eval_umma(const uint8_t* __restrict__ image, const PState* __restrict__ states
       // Linear layers: sum the per-position partials of each board in a FIXED order (deterministic results,
       // independent of how leaves were batched), in two levels: (board, row, output) over the columns and both
       // channel halves, then (board, output) over the rows.
-      for (int i = et; i < (int)nb * G::ROWS * 16; i += EPI_THREADS) {
+      for (int i = et; i < (int)nb * G::ROWS * 16; i += 256) {
         const int a = i & 15, br = i >> 4, bi = br / G::ROWS, r = br % G::ROWS;
         if (a <= G::A) {
           float acc = 0.0f;
@@ -664,7 +603,7 @@ k_eval_umma(const uint8_t* __restrict__ image, const PState* __restrict__ states
         }
       }
       epi_bar_sync();
-      for (int i = et; i < (int)nb * 16; i += EPI_THREADS) {
+      for (int i = et; i < (int)nb * 16; i += 256) {
         const int bi = i >> 4, a = i & 15;
         if (a <= G::A) {
           float acc = 0.0f;
@@ -693,17 +632,12 @@ k_eval_umma(const uint8_t* __restrict__ image, const PState* __restrict__ states
           for (int a = 0; a < G::A; ++a) logits_out[(size_t)slot * G::A + a] = lg[a];
         }
       }
-      epi_bar_sync();                                              // s_logits / s_part are reused by the next batch
-#ifdef SPB_PROFILE
-      prof_acc2 += clock64() - prof_t1;                            // head layer + staging of the next batch + finish
-#endif
+      epi_bar_sync();                                              // s_logits / s_states are reused by the next batch
     }
 #ifdef SPB_PROFILE
     if (et == 0) {
       g_eval_prof[blockIdx.x][3] = clock64() - prof_start;     // epilogue warp total
       g_eval_prof[blockIdx.x][4] = prof_acc0;                  // waiting for accumulators (MMA)
-      g_eval_prof[blockIdx.x][6] = prof_acc1;                  // layer epilogue bodies (after the wait)
-      g_eval_prof[blockIdx.x][7] = prof_acc2;                  // head + staging + finish (incl. its waits)
     }
 #endif
   }
@@ -734,8 +668,13 @@ static cudaError_t launch_t(const Evaluator::DevNet& net, const PState* states, 
 }
 
 #ifdef SPB_PROFILE
-extern "C" int spb_debug_set(int v) { return (int)cudaMemcpyToSymbol(g_eval_debug, &v, sizeof v); }
-extern "C" int spb_debug_eval_profile(unsigned long long* out, int n_ctas) {
+extern "C" int spb_debug_set_v1(int v) { return (int)cudaMemcpyToSymbol(g_eval_debug, &v, sizeof v); }
+extern "C" int spb_debug_eval_profile_layers_v1(unsigned long long* out, int n_ctas, int reset) {
+  int rc = (int)cudaMemcpyFromSymbol(out, g_eval_prof_layer, sizeof(unsigned long long) * 24 * (size_t)n_ctas);
+  if (reset) { static unsigned long long z[160 * 24]; rc |= (int)cudaMemcpyToSymbol(g_eval_prof_layer, z, sizeof z); }
+  return rc;
+}
+extern "C" int spb_debug_eval_profile_v1(unsigned long long* out, int n_ctas) {
   return (int)cudaMemcpyFromSymbol(out, g_eval_prof, sizeof(unsigned long long) * 8 * (size_t)n_ctas);
 }
 #endif
@@ -746,5 +685,5 @@ cudaError_t launch(const Evaluator::DevNet& net, int game, const PState* states,
   return launch_t<TicTacToe>(net, states, list, count_dev, max_n, out, stride, logits_out, stream);
 }
 
-}  // namespace umma
+}  // namespace umma_v1
 }  // namespace spb

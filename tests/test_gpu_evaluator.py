@@ -44,6 +44,12 @@ def test_tcgen05_evaluator_matches_torch(game, n):
     _check(game, 0, n, 2, torch_net.to_safetensors_tch)
 
 
+@pytest.mark.parametrize("game", [S.GAME_C4, S.GAME_TTT], ids=["c4", "ttt"])
+@pytest.mark.parametrize("n", [1, 19, 2000])
+def test_tcgen05_dx_sharing_variant_matches_torch(game, n):
+    _check(game, S.FLAG_EVAL_DX, n, 2, torch_net.to_safetensors_tch)
+
+
 def test_tcgen05_and_simt_agree_closely():
     lg0, v0 = _check(S.GAME_C4, 0, 257, 4, torch_net.to_safetensors_explicit)
     lg1, v1 = _check(S.GAME_C4, S.FLAG_EVAL_SIMT, 257, 4, torch_net.to_safetensors_explicit)

@@ -12,18 +12,14 @@ with S.Engine(game=S.GAME_C4, num_games=G, evaluator=S.EVAL_NET, flags=S.FLAG_NO
     e.reset_games(roots)
     e.search(sims)
     L = S.load_library()
-    lay = np.zeros((148, 24), np.uint64)
-    L.spb_debug_eval_profile_layers(C.c_void_p(lay.ctypes.data), 148, 1)
-    for dbg in (0,):
-        L.spb_debug_set(dbg)
-        ms, n, fl = e.time_evaluator(10)
-        buf = np.zeros((148, 8), np.uint64)
-        L.spb_debug_eval_profile(C.c_void_p(buf.ctypes.data), 148)
-        b = buf.astype(np.float64)
-        print("dbg %d: eval ms %.3f positions %d | MMA warp total %.0f, wait epi %.0f (%.0f%%), wait weights %.0f (%.0f%%) | epi total %.0f wait MMA %.0f (%.0f%%)" % (
-            dbg, ms, n, b[:, 0].mean(), b[:, 1].mean(), 100 * b[:, 1].mean() / b[:, 0].mean(), b[:, 5].mean(), 100 * b[:, 5].mean() / b[:, 0].mean(),
-            b[:, 3].mean(), b[:, 4].mean(), 100 * b[:, 4].mean() / b[:, 3].mean()), flush=True)
-        L.spb_debug_eval_profile_layers(C.c_void_p(lay.ctypes.data), 148, 1)
-        lm = lay.astype(np.float64).mean(0) / 12.0   # 12 launches (2 warm-up + 10)
-        print("per-launch MMA-warp wait for activations by layer:", [int(x) for x in lm[:10]])
-        print("per-launch MMA-warp wait for weights by layer:    ", [int(x) for x in lm[10:20]])
+    for dbg in (0, 4, 7):
+      L.spb_debug_set(dbg)
+      ms, n, fl = e.time_evaluator(10)
+      print('dbg', dbg)
+      buf = np.zeros((148, 8), np.uint64)
+      L.spb_debug_eval_profile(C.c_void_p(buf.ctypes.data), 148)
+      b = buf.astype(np.float64)
+      print("eval ms %.3f positions %d | MMA warp total %.0f, wait epi %.0f (%.0f%%), wait weights %.0f (%.0f%%) | epi total %.0f wait MMA %.0f (%.0f%%)" % (
+        ms, n, b[:, 0].mean(), b[:, 1].mean(), 100 * b[:, 1].mean() / b[:, 0].mean(), b[:, 5].mean(), 100 * b[:, 5].mean() / b[:, 0].mean(),
+        b[:, 3].mean(), b[:, 4].mean(), 100 * b[:, 4].mean() / b[:, 3].mean()), flush=True)
+      print("epilogue layer bodies total %.0f ; head+stage+finish total %.0f ; batches %.0f" % (b[:, 6].mean(), b[:, 7].mean(), b[:, 2].mean()))
