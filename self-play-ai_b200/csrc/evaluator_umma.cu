@@ -21,7 +21,7 @@
 //                  out[p]  = E_0[p-1] + E_1[p] + E_2[p+1]               (epilogue: +-1-lane warp shuffles)
 //              Rows 32k-1 are pad cells (W8 divides 32), where E is identically 0 and the output is forced to
 //              0, so no value ever crosses a warp or tile boundary.
-//   B operand  weights of one (ky, k-step): bf16 [2 chunks][3N rows][8], 6 KB, streamed into a 12-slot ring by
+//   B operand  weights of one (ky, k-step): bf16 [2 chunks][3N rows][8], 6 KB, streamed through a 14-slot rotating ring by
 //              cp.async.bulk (TMA, 1-D) from an L2-resident image; BatchNorm is folded in on the host.
 //   D          fp32 accumulators in TMEM: two sets of 192 columns, ping-ponged per tile.
 //   epilogue   16 warps (four per TMEM lane quadrant, 16 channels each): tcgen05.ld of the three kx blocks,
@@ -50,8 +50,9 @@ struct Geo {
   static constexpr int BS = W8 * RP;                         // rows per board (56 / 16)
   static constexpr int NT = 4;                               // tiles per batch
   static constexpr int NB = (NT * 128) / BS;                 // boards per batch (9 / 32)
-  static constexpr int LEAD = 16;                            // zero rows in front (a kernel row reaches back W8)
-  static constexpr int Q = LEAD + NT * 128 + 16;             // rows of an activation buffer
+  static constexpr int LEAD = 8;                             // zero rows in front (a kernel row reaches back W8 <= 8)
+  static constexpr int Q = LEAD + NT * 128 + 8;              // rows of an activation buffer
+  static constexpr int NS = (G::COLS == 7) ? 14 : 13;        // weight ring slots: one layer (12 blocks) + spare slots, see ring comment
   static constexpr int P = G::ROWS * G::COLS;
   static constexpr int APAD = (G::A <= 8) ? 8 : 16;          // policy FC weights per (pos, channel), bf16
 };
@@ -59,7 +60,8 @@ struct Geo {
 constexpr int N_LAYERS = 10;          // stem, 8 residual convs, fused head conv
 constexpr int HEAD_N = 48;            // 32 policy + 3 value + 13 zero output channels
 constexpr int SLOT_BYTES = 6144;      // one (ky, k-step) block of a 64->64 layer: 2 chunks x 192 rows x 16 B
-constexpr int N_SLOTS = 12;           // 3 kernel rows x 4 k-steps = one whole layer
+constexpr int LAYER_BLOCKS = 12;      // 3 kernel rows x 4 k-steps = one whole layer (the stem has 3)
+constexpr int MAX_SLOTS = 14;
 
 __host__ __device__ constexpr int layer_n(int l) { return l == 9 ? HEAD_N : 64; }
 __host__ __device__ constexpr int layer_ksteps(int l) { return l == 0 ? 1 : 4; }
@@ -234,9 +236,9 @@ __device__ __forceinline__ uint32_t relu_bf16x2(uint32_t v) {
 // Issues the 3 kernel rows x KSTEPS MMAs of one (layer, tile).  A descriptor low word = a_lo_tile + row shift +
 // k-step * 2Q (two K chunks further); B = ring slot (ky, kk).  Descriptor high words are constants
 // (SBO = 128 B, version 1).  K-major SWIZZLE_NONE: LBO = byte stride between the two K chunks of one MMA.
-template <int W8, int Q, int KSTEPS, int N>
+template <int W8, int Q, int KSTEPS, int N, int NS>
 __device__ __forceinline__ void issue_tile(bool issuer, uint32_t a_lo_tile, uint32_t b_lo_base, uint32_t d_tmem,
-                                           bool first_tile, bool last_tile, uint32_t w_par_mask, uint32_t bar_base,
+                                           bool first_tile, bool last_tile, uint32_t blk_base, uint32_t bar_base,
                                            unsigned long long& prof_wfull) {
   constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);
   constexpr uint32_t IDESC = make_idesc(3 * N);
@@ -244,12 +246,14 @@ __device__ __forceinline__ void issue_tile(bool issuer, uint32_t a_lo_tile, uint
   for (int ky = 0; ky < 3; ++ky) {
 #pragma unroll
     for (int kk = 0; kk < KSTEPS; ++kk) {
-      const int slot = ky * 4 + kk;
+      // Blocks go through the ring in stream order: block number -> slot = number % NS, fill = number / NS.
+      const uint32_t blk = blk_base + (uint32_t)(ky * KSTEPS + kk);
+      const uint32_t slot = blk % NS, fill = blk / NS;
       if (first_tile) {                                                                          // w_full[slot]
 #ifdef SPB_PROFILE
         const unsigned long long t0 = clock64();
 #endif
-        mbar_wait(bar_base + (uint32_t)slot * 8u, (w_par_mask >> slot) & 1u);
+        mbar_wait(bar_base + slot * 8u, fill & 1u);
 #ifdef SPB_PROFILE
         prof_wfull += clock64() - t0;
 #endif
@@ -257,11 +261,11 @@ __device__ __forceinline__ void issue_tile(bool issuer, uint32_t a_lo_tile, uint
       }
       if (issuer) {
         const uint32_t a_lo = a_lo_tile + (uint32_t)((ky - 1) * W8 + kk * 2 * Q);
-        const uint32_t b_lo = (b_lo_base + (uint32_t)slot * (SLOT_BYTES >> 4)) | ((uint32_t)(3 * N) << 16);
+        const uint32_t b_lo = (b_lo_base + slot * (SLOT_BYTES >> 4)) | ((uint32_t)(3 * N) << 16);
         const uint64_t ad = ((uint64_t)DESC_HI << 32) | a_lo;
         const uint64_t bd = ((uint64_t)DESC_HI << 32) | b_lo;
         umma_f16(d_tmem, ad, bd, IDESC, (ky | kk) != 0);
-        if (last_tile) umma_commit(bar_base + (uint32_t)(N_SLOTS + slot) * 8u);                  // w_empty[slot]
+        if (last_tile) umma_commit(bar_base + (uint32_t)(MAX_SLOTS + slot) * 8u);                // w_empty[slot]
       }
       __syncwarp();
     }
@@ -277,15 +281,15 @@ struct Smem {
   static constexpr int ACT_BYTES = 8 * Ge::Q * 16;                 // 69,632
   static constexpr int OFF_ACT0 = 0;
   static constexpr int OFF_ACT1 = ACT_BYTES;
-  static constexpr int OFF_W = 2 * ACT_BYTES;                      // 12 x 6 KB weight ring
-  static constexpr int OFF_BIAS = OFF_W + N_SLOTS * SLOT_BYTES;    // 10 x 64 f32
+  static constexpr int OFF_W = 2 * ACT_BYTES;                      // NS x 6 KB weight ring
+  static constexpr int OFF_BIAS = OFF_W + Ge::NS * SLOT_BYTES;     // 10 x 64 f32
   static constexpr int OFF_LOGITS = OFF_BIAS + N_LAYERS * 64 * 4;  // [NB][16] f32
   static constexpr int OFF_PART = OFF_LOGITS + Ge::NB * 16 * 4;    // [NB][ROWS][16] f32 row partials of the Linear layers
   static constexpr int OFF_STATES = OFF_PART + Ge::NB * G::ROWS * 16 * 4;   // [2][NB] PState
   static constexpr int OFF_SLOTS = OFF_STATES + 2 * Ge::NB * 16;   // [2][NB] u32
   static constexpr int OFF_BARS = (OFF_SLOTS + 2 * Ge::NB * 4 + 15) & ~15;
-  // barriers: w_full[12], w_empty[12], acc_full[2], acc_empty[2], act_ready[4], stage_ready[4]
-  static constexpr int N_BARS = 2 * N_SLOTS + 4 + 2 * Ge::NT;
+  // barriers: w_full[14], w_empty[14], acc_full[2], acc_empty[2], act_ready[4], stage_ready[4]
+  static constexpr int N_BARS = 2 * MAX_SLOTS + 4 + 2 * Ge::NT;
   static constexpr int OFF_TMEM = OFF_BARS + N_BARS * 8;
   static constexpr int TOTAL = OFF_TMEM + 16;
 };
@@ -326,13 +330,13 @@ k_eval_umma(const uint8_t* __restrict__ image, const PState* __restrict__ states
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t s_base = smem_u32(smem);
   const uint32_t bar_base = s_base + Sm::OFF_BARS;
-  auto bar_w_empty = [&](int s) { return bar_base + (uint32_t)(N_SLOTS + s) * 8u; };
-  auto bar_acc_full = [&](uint32_t set) { return bar_base + (uint32_t)(2 * N_SLOTS + set) * 8u; };
-  auto bar_acc_empty = [&](uint32_t set) { return bar_base + (uint32_t)(2 * N_SLOTS + 2 + set) * 8u; };
-  auto bar_act_ready = [&](int t) { return bar_base + (uint32_t)(2 * N_SLOTS + 4 + t) * 8u; };
+  auto bar_w_empty = [&](int s) { return bar_base + (uint32_t)(MAX_SLOTS + s) * 8u; };
+  auto bar_acc_full = [&](uint32_t set) { return bar_base + (uint32_t)(2 * MAX_SLOTS + set) * 8u; };
+  auto bar_acc_empty = [&](uint32_t set) { return bar_base + (uint32_t)(2 * MAX_SLOTS + 2 + set) * 8u; };
+  auto bar_act_ready = [&](int t) { return bar_base + (uint32_t)(2 * MAX_SLOTS + 4 + t) * 8u; };
   // The staged input of a batch has its own barrier: it may complete while act_ready's previous phase is still
   // being consumed by the MMA warp (an mbarrier must never run two phases ahead of a waiter).
-  auto bar_stage_ready = [&](int t) { return bar_base + (uint32_t)(2 * N_SLOTS + 4 + Ge::NT + t) * 8u; };
+  auto bar_stage_ready = [&](int t) { return bar_base + (uint32_t)(2 * MAX_SLOTS + 4 + Ge::NT + t) * 8u; };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + Sm::OFF_TMEM);
 
   // ---- one-time setup -----------------------------------------------------------------------------
@@ -345,7 +349,7 @@ k_eval_umma(const uint8_t* __restrict__ image, const PState* __restrict__ states
     for (int i = tid; i < N_LAYERS * 64; i += THREADS) sb[i] = gb[i];
   }
   if (tid == 0) {
-    for (int s = 0; s < N_SLOTS; ++s) { mbar_init(bar_base + (uint32_t)s * 8u, 1); mbar_init(bar_w_empty(s), 1); }
+    for (int s = 0; s < MAX_SLOTS; ++s) { mbar_init(bar_base + (uint32_t)s * 8u, 1); mbar_init(bar_w_empty(s), 1); }
     for (uint32_t s = 0; s < 2; ++s) { mbar_init(bar_acc_full(s), 1); mbar_init(bar_acc_empty(s), EPI_WARPS); }
     for (int t = 0; t < Ge::NT; ++t) { mbar_init(bar_act_ready(t), EPI_WARPS); mbar_init(bar_stage_ready(t), EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -360,22 +364,23 @@ k_eval_umma(const uint8_t* __restrict__ image, const PState* __restrict__ states
   const uint32_t n_batches = (my_end - my_begin + Ge::NB - 1) / Ge::NB;
 
   if (warp == 0) {
-    // ===== weight producer: streams (layer, ky, k-step) blocks into the 12-slot ring ===================
+    // ===== weight producer: streams (layer, ky, k-step) blocks through the NS-slot ring ==================
+    // The ring has one or two slots more than a layer has blocks and blocks take slots in stream order, so the
+    // first blocks of the next layer land in slots this layer does not use (prefetched a whole layer ahead) and
+    // every later block gets a little more than one tile time between its slot's release and its first use.
     if (lane == 0) {
-      uint32_t filled = 0, par = 0;                                // per slot: ever filled / parity of its next release
+      uint32_t blk = 0;                                            // blocks streamed so far
       for (uint32_t b = 0; b < n_batches; ++b) {
         for (int l = 0; l < N_LAYERS; ++l) {
-          const int KS = layer_ksteps(l);
+          const int nblk = 3 * layer_ksteps(l);
           const uint32_t bytes = (uint32_t)layer_block_bytes(l);
           const uint8_t* src = image + layer_offset(l);
-          for (int ky = 0; ky < 3; ++ky)
-            for (int kk = 0; kk < KS; ++kk) {
-              const int s = ky * 4 + kk;
-              if ((filled >> s) & 1u) { mbar_wait(bar_w_empty(s), (par >> s) & 1u); par ^= 1u << s; }
-              filled |= 1u << s;
-              mbar_expect_tx(bar_base + (uint32_t)s * 8u, bytes);
-              bulk_g2s(s_base + Sm::OFF_W + (uint32_t)s * SLOT_BYTES, src + (size_t)(ky * KS + kk) * bytes, bytes, bar_base + (uint32_t)s * 8u);
-            }
+          for (int i = 0; i < nblk; ++i, ++blk) {
+            const uint32_t s = blk % Ge::NS, fill = blk / Ge::NS;
+            if (fill > 0) mbar_wait(bar_w_empty((int)s), (fill - 1u) & 1u);
+            mbar_expect_tx(bar_base + s * 8u, bytes);
+            bulk_g2s(s_base + Sm::OFF_W + s * SLOT_BYTES, src + (size_t)i * bytes, bytes, bar_base + s * 8u);
+          }
         }
       }
     }
@@ -391,7 +396,7 @@ k_eval_umma(const uint8_t* __restrict__ image, const PState* __restrict__ states
       unsigned long long prof_w = 0;
       const bool issuer = elect_one();
       const uint32_t b_lo_base = ((s_base + Sm::OFF_W) >> 4);
-      uint32_t w_par = 0;      // bit s: parity of the next fill of ring slot s
+      uint32_t blk_base = 0;   // number of weight blocks of all previous layers (ring position of this layer's block 0)
       uint32_t act_par = 0;    // bit t: parity of the next completion of act_ready[t]
       uint32_t stage_par = 0;  // same for stage_ready[t]
       uint32_t tile_ctr = 0;   // tiles issued so far; accumulator set = tile_ctr & 1
@@ -403,7 +408,6 @@ k_eval_umma(const uint8_t* __restrict__ image, const PState* __restrict__ states
           const uint32_t a_lo_base = ((in_buf >> 4) + Ge::LEAD) | ((uint32_t)Ge::Q << 16);
           const uint32_t cur_par = (l == 0) ? stage_par : act_par;
           if (l == 0) stage_par ^= (1u << nt) - 1u; else act_par ^= (1u << nt) - 1u;
-          const uint32_t slots_used = (l == 0) ? 0x111u : 0xFFFu;
           for (int t = 0; t < nt; ++t, ++tile_ctr) {
             const int wt = min(t + 1, nt - 1);                   // epilogue runs tiles in order: tile wt done => 0..wt done
             const uint32_t set = tile_ctr & 1u;
@@ -415,13 +419,13 @@ k_eval_umma(const uint8_t* __restrict__ image, const PState* __restrict__ states
             const uint32_t a_lo_tile = a_lo_base + (uint32_t)t * 128u;
             const uint32_t d_tmem = tmem_base + set * (uint32_t)ACC_COLS;
             const bool first = (t == 0), last = (t == nt - 1);
-            if (l == 0)      issue_tile<Ge::W8, Ge::Q, 1, 64>(issuer, a_lo_tile, b_lo_base, d_tmem, first, last, w_par, bar_base, prof_w);
-            else if (l < 9)  issue_tile<Ge::W8, Ge::Q, 4, 64>(issuer, a_lo_tile, b_lo_base, d_tmem, first, last, w_par, bar_base, prof_w);
-            else             issue_tile<Ge::W8, Ge::Q, 4, HEAD_N>(issuer, a_lo_tile, b_lo_base, d_tmem, first, last, w_par, bar_base, prof_w);
+            if (l == 0)      issue_tile<Ge::W8, Ge::Q, 1, 64, Ge::NS>(issuer, a_lo_tile, b_lo_base, d_tmem, first, last, blk_base, bar_base, prof_w);
+            else if (l < 9)  issue_tile<Ge::W8, Ge::Q, 4, 64, Ge::NS>(issuer, a_lo_tile, b_lo_base, d_tmem, first, last, blk_base, bar_base, prof_w);
+            else             issue_tile<Ge::W8, Ge::Q, 4, HEAD_N, Ge::NS>(issuer, a_lo_tile, b_lo_base, d_tmem, first, last, blk_base, bar_base, prof_w);
             if (issuer) umma_commit(bar_acc_full(set));
             __syncwarp();
           }
-          w_par ^= slots_used;
+          blk_base += (uint32_t)(3 * layer_ksteps(l));
         }
       }
 #ifdef SPB_PROFILE
@@ -500,23 +504,13 @@ k_eval_umma(const uint8_t* __restrict__ image, const PState* __restrict__ states
         uint8_t* dst_buf = smem + (in0 ? Sm::OFF_ACT1 : Sm::OFF_ACT0);
         const bool has_skip = (l >= 2 && (l & 1) == 0 && l <= 8);   // second conv of a residual block
         if (l < 9) {
-          float bias_r[16];                                         // this thread's 16 output channels
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float4 bv = *reinterpret_cast<const float4*>(s_bias + l * 64 + cg * 16 + q * 4);
-            bias_r[4 * q] = bv.x; bias_r[4 * q + 1] = bv.y; bias_r[4 * q + 2] = bv.z; bias_r[4 * q + 3] = bv.w;
-          }
+          const float* bias_p = s_bias + l * 64 + cg * 16;          // this thread's 16 output channels
           for (int t = 0; t < nt; ++t, ++tile_ctr) {
             const uint32_t set = tile_ctr & 1u;
             const int m = t * 128 + row_in_tile;
             const int bi = m / Ge::BS, rem = m % Ge::BS, r = rem / Ge::W8, c = rem % Ge::W8;
             const bool valid = (uint32_t)bi < nb && r < G::ROWS && c < G::COLS;
             uint8_t* drow = dst_buf + (size_t)(cg * 2) * Ge::Q * 16 + (size_t)(Ge::LEAD + m) * 16;   // chunk 2*cg
-            uint4 sk[2];
-            if (has_skip) {                                         // (x + f(x)).relu(), model/mod.rs:163
-              sk[0] = *reinterpret_cast<const uint4*>(drow);
-              sk[1] = *reinterpret_cast<const uint4*>(drow + (size_t)Ge::Q * 16);
-            }
             PROF_BEGIN();
             warp_wait(bar_acc_full(set), (tile_ctr >> 1) & 1u, lane);
             PROF_END(prof_acc0);
@@ -524,30 +518,32 @@ k_eval_umma(const uint8_t* __restrict__ image, const PState* __restrict__ states
             prof_t1 = clock64();
 #endif
             tc_fence_after();
+            // Drain the whole accumulator slice first and hand the set back to the MMA warps at once (there are
+            // only two sets, so the tile after next is waiting for this one); the math comes afterwards.
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + set * (uint32_t)ACC_COLS + (uint32_t)cg * 16u;
+            uint32_t em[16], e0[16], ep[16];
+            tmem_ld16(taddr, em);                                   // kx = 0 block: E_0
+            tmem_ld16(taddr + 64, e0);                              // kx = 1 block: E_1
+            tmem_ld16(taddr + 128, ep);                             // kx = 2 block: E_2
+            tmem_ld_wait();
+            tc_fence_before();
+            warp_arrive(bar_acc_empty(set), lane);
 #pragma unroll
             for (int j = 0; j < 2; ++j) {                           // one 8-channel chunk = one 16-B store
-              uint32_t em[8], e0[8], ep[8];
-              if (!DBG(1)) {
-                tmem_ld8(taddr + j * 8, em);                        // kx = 0 block: E_0
-                tmem_ld8(taddr + 64 + j * 8, e0);                   // kx = 1 block: E_1
-                tmem_ld8(taddr + 128 + j * 8, ep);                  // kx = 2 block: E_2
-                tmem_ld_wait();
-              } else {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) em[e] = e0[e] = ep[e] = 0;
-              }
-              if (j == 1) {
-                tc_fence_before();
-                warp_arrive(bar_acc_empty(set), lane);              // accumulator set may be overwritten
-              }
-              if (DBG(0)) continue;
+              const float4 b0 = *reinterpret_cast<const float4*>(bias_p + j * 8), b1 = *reinterpret_cast<const float4*>(bias_p + j * 8 + 4);
               float v[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) v[e] = dx_sum(em[e], e0[e], ep[e], lane) + bias_r[j * 8 + e];
-              if (has_skip) {
-                v[0] += bf_lo(sk[j].x); v[1] += bf_hi(sk[j].x); v[2] += bf_lo(sk[j].y); v[3] += bf_hi(sk[j].y);
-                v[4] += bf_lo(sk[j].z); v[5] += bf_hi(sk[j].z); v[6] += bf_lo(sk[j].w); v[7] += bf_hi(sk[j].w);
+              v[0] = dx_sum(em[j * 8 + 0], e0[j * 8 + 0], ep[j * 8 + 0], lane) + b0.x;
+              v[1] = dx_sum(em[j * 8 + 1], e0[j * 8 + 1], ep[j * 8 + 1], lane) + b0.y;
+              v[2] = dx_sum(em[j * 8 + 2], e0[j * 8 + 2], ep[j * 8 + 2], lane) + b0.z;
+              v[3] = dx_sum(em[j * 8 + 3], e0[j * 8 + 3], ep[j * 8 + 3], lane) + b0.w;
+              v[4] = dx_sum(em[j * 8 + 4], e0[j * 8 + 4], ep[j * 8 + 4], lane) + b1.x;
+              v[5] = dx_sum(em[j * 8 + 5], e0[j * 8 + 5], ep[j * 8 + 5], lane) + b1.y;
+              v[6] = dx_sum(em[j * 8 + 6], e0[j * 8 + 6], ep[j * 8 + 6], lane) + b1.z;
+              v[7] = dx_sum(em[j * 8 + 7], e0[j * 8 + 7], ep[j * 8 + 7], lane) + b1.w;
+              if (has_skip) {                                       // (x + f(x)).relu(), model/mod.rs:163
+                const uint4 sk = *reinterpret_cast<const uint4*>(drow + (size_t)j * Ge::Q * 16);
+                v[0] += bf_lo(sk.x); v[1] += bf_hi(sk.x); v[2] += bf_lo(sk.y); v[3] += bf_hi(sk.y);
+                v[4] += bf_lo(sk.z); v[5] += bf_hi(sk.z); v[6] += bf_lo(sk.w); v[7] += bf_hi(sk.w);
               }
               uint4 o = make_uint4(0, 0, 0, 0);
               if (valid) {

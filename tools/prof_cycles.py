@@ -6,13 +6,13 @@ from selfplay_b200.synth import synthetic_roots_device
 from selfplay_b200.weights_init import random_checkpoint
 G = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 sims = int(sys.argv[2]) if len(sys.argv) > 2 else 40
-with S.Engine(game=S.GAME_C4, num_games=G, evaluator=S.EVAL_NET, flags=S.FLAG_NO_GRAPH) as e:
+with S.Engine(game=S.GAME_C4, num_games=G, evaluator=S.EVAL_NET, flags=S.FLAG_NO_GRAPH | S.FLAG_EVAL_DX) as e:
     e.load_weights(random_checkpoint(1, 0))
     roots = synthetic_roots_device(e, G)
     e.reset_games(roots)
     e.search(sims)
     L = S.load_library()
-    for dbg in (0, 4, 7):
+    for dbg in (0,):
       L.spb_debug_set(dbg)
       ms, n, fl = e.time_evaluator(10)
       print('dbg', dbg)
