@@ -265,6 +265,22 @@ def run_ours(args):
                           "frac": tree_bytes_per_sim * G / (tree_us * 1e-6) / 1e9 / peak_hbm},
         "counters": {k: ctr[k] for k in ("simulations", "evaluations", "terminal_leaves")},
     }
+    # ---- full-game leg: greedy last-max moves, subtree reuse, finished slots refilled from the same roots ------
+    if args.full_game_moves > 0:
+        eng.reset_games(roots)
+        eng.drain_trajectories()
+        barrier()
+        t0 = time.perf_counter()
+        finished = 0
+        for _ in range(args.full_game_moves):
+            eng.search(sims)                                   # carry + 800 more simulations per move (mcts.rs:161-192)
+            finished += eng.selfplay_step(S.MOVE_GREEDY_LAST_MAX, restart_roots=roots)
+        barrier()
+        fg_s = rank_max(time.perf_counter() - t0)
+        pos, _ = eng.drain_trajectories()
+        line["full_game"] = {"moves": args.full_game_moves, "value": world * G * sims * args.full_game_moves / fg_s, "unit": "sims/s",
+                             "finished_games_rank0": int(finished), "trajectory_positions_rank0": int(len(pos)),
+                             "note": "search + on-device move selection + use_subtree per move, wall clock"}
     # ---- CPU baseline beside it (rank 0, N = 1 only; bounded sample) -----------------------------------
     if world == 1 and not args.no_cpu_baseline:
         eng.close()
@@ -298,6 +314,7 @@ def main():
     ap.add_argument("--sims", type=int, default=SIMS)
     ap.add_argument("--ref-sims", type=int, default=100, help="simulations per step of the CPU arm's bounded sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--full-game-moves", type=int, default=4, help="extra leg: self-play moves with subtree reuse (0 = skip)")
     args = ap.parse_args()
     if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
         # not under torchrun: launch one rank per GPU ourselves
