@@ -37,7 +37,7 @@ constexpr int THREADS = WARPS_PER_BLOCK * 32;
 // kernels
 // ------------------------------------------------------------------------------------------------
 
-__global__ void k_reset(Trees T, const uint32_t* slots, const PState* roots, uint32_t n) {
+__global__ void k_reset(Trees T, uint32_t* hist_len, const uint32_t* slots, const PState* roots, uint32_t n) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   uint32_t g = slots ? slots[i] : i;
@@ -46,6 +46,7 @@ __global__ void k_reset(Trees T, const uint32_t* slots, const PState* roots, uin
   T.buf[g] = 0;
   T.live[g] = 1;
   T.n_nodes[g] = 1;
+  hist_len[g] = 0;   // a restarted slot starts a new trajectory (Tree::with_root_state has empty histories, mcts.rs:86-89)
   NodeRec r;
   r.N = 0; r.W = 0.0f; r.P = 0.0f;
   r.info = make_info(0, 0, ps_status(root));
@@ -956,7 +957,7 @@ int32_t spb_reset_games(spb_engine* e, const uint32_t* slots, uint32_t n, const 
     cudaError_t ce = cudaMemcpyAsync(e->d_stage, e->h_stage, bytes, cudaMemcpyHostToDevice, e->stream);
     if (ce != cudaSuccess) { e->set_error(cudaGetErrorString(ce)); return SPB_ERR_CUDA; }
     auto* ds = static_cast<uint8_t*>(e->d_stage);
-    k_reset<<<(n + 127) / 128, 128, 0, e->stream>>>(e->T, slots ? reinterpret_cast<uint32_t*>(ds) : nullptr,
+    k_reset<<<(n + 127) / 128, 128, 0, e->stream>>>(e->T, e->P.hist_len, slots ? reinterpret_cast<uint32_t*>(ds) : nullptr,
                                                     roots ? reinterpret_cast<PState*>(ds + off_roots) : nullptr, n);
     ++e->launches;
     ce = cudaGetLastError();

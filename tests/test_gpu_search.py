@@ -199,3 +199,32 @@ def test_reference_shaped_host_api():
         best = max(res[0][1], key=lambda p: (p[1], p[0]))[0]
         trees[0].use_subtree(best)
         assert trees[0].node_state(0).num_actions_played == 1
+
+
+def test_selfplay_step_temperature_sampling_distribution():
+    """learner_concurrent.rs:189-194: the move is sampled in proportion to visit_count^temperature.  The reference
+    uses the unseedable thread_rng, so only the distribution can be checked (counter-based RNG on the device)."""
+    G, sims, temp = 1024, 200, 1.25
+    with S.Engine(game=S.GAME_C4, num_games=G, evaluator=S.EVAL_DET) as e:
+        e.reset_games()
+        e.search(sims)
+        acts, counts, ids = e.root_children(0)
+        e.selfplay_step(S.MOVE_TEMPERATURE, temperature=temp, seed=12345)
+        chosen = np.zeros(7)
+        for slot in range(G):
+            st = e.get_state(slot, 0)
+            col = [c for c in range(7) if (st.stones[0] >> (c * 7)) & 1][0]
+            chosen[col] += 1
+        w = np.array([float(c) ** temp for c in counts])
+        p = np.zeros(7)
+        p[acts] = w / w.sum()
+        expected = p * G
+        assert chosen.sum() == G
+        chi2 = float((((chosen - expected) ** 2) / np.maximum(expected, 1e-9))[expected > 0].sum())
+        assert chi2 < 40, (chi2, chosen, expected)            # 6 degrees of freedom; 40 is far in the tail
+        assert np.all(chosen[expected == 0] == 0)
+        # a different seed gives a different sample; the same seed the same one
+        e.reset_games(); e.search(sims); e.selfplay_step(S.MOVE_TEMPERATURE, temperature=temp, seed=12345)
+        again = [e.get_state(s, 0).key() for s in range(64)]
+        e.reset_games(); e.search(sims); e.selfplay_step(S.MOVE_TEMPERATURE, temperature=temp, seed=12345)
+        assert again == [e.get_state(s, 0).key() for s in range(64)]
