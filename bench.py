@@ -325,6 +325,11 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
                "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:]
         return subprocess.call(cmd)
+    # stdout carries exactly ONE JSON line: libraries that write to fd 1 (NCCL prints its version there) are sent to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(json_fd, "w")
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)

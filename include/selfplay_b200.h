@@ -37,7 +37,7 @@ extern "C" {
 #define SPB_OK             0
 #define SPB_ERR_ARG       -1   /* bad argument (null pointer, slot out of range, ...) */
 #define SPB_ERR_CUDA      -2   /* CUDA runtime error / no sm_100 device */
-#define SPB_ERR_POOL      -3   /* a tree's node pool is full (max_nodes_per_tree) */
+#define SPB_ERR_POOL      -3   /* a tree's node pool is full and cannot grow (SPB_FLAG_FIXED_POOL, HBM, 2^24) */
 #define SPB_ERR_ILLEGAL   -4   /* illegal move / game already ended (ref: connect_four.rs:193,209) */
 #define SPB_ERR_WEIGHTS   -5   /* weight blob malformed / tensor missing / shape mismatch */
 #define SPB_ERR_STATE     -6   /* call not valid in the engine's current state */
@@ -83,7 +83,7 @@ typedef struct spb_config {
   int32_t  game;                 /* SPB_GAME_* */
   int32_t  device;               /* CUDA device ordinal */
   uint32_t num_games;            /* G: concurrent trees ("slots"); ref: mcts.rs:54 num_parallel_self_play_games */
-  uint32_t max_nodes_per_tree;   /* arena capacity per tree; 0 = default (16384) */
+  uint32_t max_nodes_per_tree;   /* initial arena capacity per tree; 0 = default (16384); grows on demand */
   uint32_t leaves_per_tree;      /* K in-flight leaves per tree per step (1..16); 1 = the reference algorithm.
                                     K > 1 is an EXTENSION (virtual loss, defined in DESIGN.md §4.4): not in the reference */
   float    c;                    /* PUCT constant; ref: mcts.rs:49 (2.0) */
@@ -98,6 +98,9 @@ typedef struct spb_config {
 #define SPB_FLAG_EVAL_SIMT  2u   /* use the CUDA-core evaluator kernel instead of tcgen05 (debug / cross-check) */
 #define SPB_FLAG_EVAL_DX    8u   /* experimental tcgen05 evaluator variant: the three kx taps of a kernel row share one A read (N = 192)
                                     and the dx shift moves into the epilogue as warp shuffles */
+#define SPB_FLAG_FIXED_POOL 16u  /* never grow the node pools: a tree that would pass max_nodes_per_tree makes spb_search return
+                                    SPB_ERR_POOL.  Without the flag the pools grow before a search that could outgrow them, like
+                                    the reference's Vec arena (mcts.rs:19) */
 #define SPB_FLAG_FORCE_SPLIT 4u  /* run DetEval / uniform through the lock-step select -> evaluate -> expand pipeline
                                     of the network evaluator instead of the fused single-kernel search */
 

@@ -423,6 +423,11 @@ __global__ void k_nodes_live(Trees T, unsigned long long* out) {
   if (g < T.G && T.live[g]) atomicAdd(out, (unsigned long long)T.n_nodes[g]);
 }
 
+__global__ void k_max_nodes(Trees T, unsigned long long* out) {
+  uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < T.G && T.live[g]) atomicMax(out, (unsigned long long)T.n_nodes[g]);
+}
+
 // ---- State trait, batched (ref: game/mod.rs:21-33) ------------------------------------------------
 template <class G>
 __global__ void k_game_next(const PState* in, const uint8_t* actions, uint32_t n, PState* out, int32_t* err) {
@@ -615,6 +620,7 @@ struct spb_engine {
     *p = static_cast<T_*>(q);
     return SPB_OK;
   }
+  int32_t ensure_capacity(uint32_t num_searches);
   int32_t ensure_stage(size_t bytes) {
     if (bytes > h_stage_bytes) {
       if (h_stage) cudaFreeHost(h_stage);
@@ -724,6 +730,60 @@ void spb_engine::destroy() {
   if (stream) cudaStreamDestroy(stream);
 }
 
+// The reference's arena is a Vec that grows without bound (mcts.rs:19,151-157).  Here every tree owns a fixed
+// slice of the pools, so before a search the slices are widened if the largest live tree could outgrow them:
+// one simulation appends at most A children (mcts.rs:131-158).  Growth is a strided device copy; it happens
+// before any tree is touched, so a failure leaves the engine as it was.
+int32_t spb_engine::ensure_capacity(uint32_t num_searches) {
+  unsigned long long mx = 0;
+  SPB_CUDA(cudaMemsetAsync(d_misc, 0, 8, stream));
+  k_max_nodes<<<(T.G + 127) / 128, 128, 0, stream>>>(T, d_misc);
+  SPB_CHECK_LAUNCH();
+  ++launches;
+  SPB_CUDA(cudaMemcpyAsync(&mx, d_misc, 8, cudaMemcpyDeviceToHost, stream));
+  SPB_CUDA(cudaStreamSynchronize(stream));
+  const unsigned long long need = mx + (unsigned long long)num_searches * (unsigned long long)A;
+  if (need <= T.cap || (cfg.flags & SPB_FLAG_FIXED_POOL)) return SPB_OK;   // fixed pool: the device flag reports exhaustion
+  unsigned long long ncap = std::max<unsigned long long>(need, 2ull * T.cap);
+  ncap = (ncap + 1023ull) & ~1023ull;
+  if (ncap > MAX_CAP) ncap = MAX_CAP;
+  if (need > ncap) { set_error("node pool exhausted: a tree would exceed 2^24 nodes"); return SPB_ERR_POOL; }
+  const size_t pool = (size_t)T.G * (size_t)ncap;
+  NodeRec* nrec[2] = {nullptr, nullptr};
+  uint32_t* npar[2] = {nullptr, nullptr};
+  cudaError_t ce = cudaSuccess;
+  for (int b = 0; b < 2 && ce == cudaSuccess; ++b) {
+    ce = cudaMalloc((void**)&nrec[b], pool * sizeof(NodeRec));
+    if (ce == cudaSuccess) ce = cudaMalloc((void**)&npar[b], pool * sizeof(uint32_t));
+  }
+  for (int b = 0; b < 2 && ce == cudaSuccess; ++b) {
+    ce = cudaMemcpy2DAsync(nrec[b], ncap * sizeof(NodeRec), T.rec[b], (size_t)T.cap * sizeof(NodeRec), (size_t)T.cap * sizeof(NodeRec), T.G,
+                           cudaMemcpyDeviceToDevice, stream);
+    if (ce == cudaSuccess)
+      ce = cudaMemcpy2DAsync(npar[b], ncap * sizeof(uint32_t), T.par[b], (size_t)T.cap * sizeof(uint32_t), (size_t)T.cap * sizeof(uint32_t), T.G,
+                             cudaMemcpyDeviceToDevice, stream);
+  }
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(stream);
+  if (ce != cudaSuccess) {
+    for (int b = 0; b < 2; ++b) { if (nrec[b]) cudaFree(nrec[b]); if (npar[b]) cudaFree(npar[b]); }
+    cudaGetLastError();
+    set_error(std::string("node pool exhausted: cannot grow the pools to ") + std::to_string(ncap) + " nodes per tree (" + cudaGetErrorString(ce) + ")");
+    return SPB_ERR_POOL;
+  }
+  for (int b = 0; b < 2; ++b) {
+    for (void* old : {(void*)T.rec[b], (void*)T.par[b]}) {
+      allocs.erase(std::find(allocs.begin(), allocs.end(), old));
+      cudaFree(old);
+    }
+    T.rec[b] = nrec[b]; T.par[b] = npar[b];
+    allocs.push_back(nrec[b]); allocs.push_back(npar[b]);
+  }
+  T.cap = (uint32_t)ncap;
+  cfg.max_nodes_per_tree = T.cap;
+  if (step_graph) { cudaGraphExecDestroy(step_graph); step_graph = nullptr; }   // the graph captured the old pointers
+  return SPB_OK;
+}
+
 int32_t spb_engine::check_device_errors() {
   uint32_t e = 0;
   SPB_CUDA(cudaMemcpyAsync(&e, T.error, 4, cudaMemcpyDeviceToHost, stream));
@@ -759,6 +819,7 @@ int32_t spb_engine::search_t(uint32_t num_searches) {
   const uint32_t blocks = (T.G + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
   const bool split = cfg.evaluator == SPB_EVAL_NET || (cfg.flags & SPB_FLAG_FORCE_SPLIT) || T.K > 1;
   if (cfg.evaluator == SPB_EVAL_NET && !evaluator.loaded()) { set_error("no weights loaded: call spb_load_weights first"); return SPB_ERR_STATE; }
+  { int32_t rc = ensure_capacity(num_searches); if (rc != SPB_OK) return rc; }
   SPB_CUDA(cudaEventRecord(ev0, stream));
   last_eval_launches = 0;
   if (!split) {

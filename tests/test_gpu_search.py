@@ -176,8 +176,8 @@ def test_selfplay_step_trajectories_match_oracle():
     assert k == len(pos)
 
 
-def test_pool_exhaustion_is_an_error_not_ub():
-    with S.Engine(game=S.GAME_C4, num_games=2, evaluator=S.EVAL_DET, max_nodes_per_tree=64) as e:
+def test_fixed_pool_exhaustion_is_an_error_not_ub():
+    with S.Engine(game=S.GAME_C4, num_games=2, evaluator=S.EVAL_DET, max_nodes_per_tree=64, flags=S.FLAG_FIXED_POOL) as e:
         e.reset_games()
         with pytest.raises(S.EngineError) as ei:
             e.search(200)
@@ -185,6 +185,33 @@ def test_pool_exhaustion_is_an_error_not_ub():
         e.reset_games()
         e.search(5)                                  # engine stays usable
         assert sum(e.root_children(0)[1]) == 4
+
+
+@pytest.mark.parametrize("flags", [0, S.FLAG_FORCE_SPLIT], ids=["fused", "split-graph"])
+def test_pools_grow_like_the_reference_arena(flags):
+    """mcts.rs:19 — the reference's arena is an unbounded Vec.  Starting from 16 nodes per tree, the pools are widened
+    before each search that could outgrow them and the trees stay bit-identical to the oracle, re-roots included."""
+    G = 6
+    roots = synthetic_roots(S.GAME_C4, G, start=40, max_ply=6)
+    f = O.Forest(O.GAME_C4, G)
+    f.reset(roots)
+    with S.Engine(game=S.GAME_C4, num_games=G, evaluator=S.EVAL_DET, max_nodes_per_tree=16, flags=flags) as e:
+        e.reset_games(roots)
+        for sims in (40, 300, 150, 700):
+            e.search(sims)
+            f.search(sims, O.EVAL_DET)
+            picks = []
+            for slot in range(G):
+                _assert_same_tree(e, f, slot, full=False)
+                acts, counts, ids = f.root_children(slot)
+                assert ids, "roots this shallow cannot finish within four moves"
+                best = max(range(len(ids)), key=lambda j: (counts[j], j))
+                picks.append(ids[best])
+            e.advance(picks)
+            for slot in range(G):
+                f.use_subtree(slot, picks[slot])
+                _assert_same_tree(e, f, slot, full=False)
+        assert max(e.arena_len(s) for s in range(G)) > 2048
 
 
 def test_reference_shaped_host_api():
