@@ -34,6 +34,7 @@
 #include <cuda_bf16.h>
 
 #include <cstring>
+#include <mutex>
 
 #include "evaluator_umma.cuh"
 
@@ -713,15 +714,23 @@ k_eval_umma(const uint8_t* __restrict__ image, const PState* __restrict__ states
 template <class G>
 static cudaError_t launch_t(const Evaluator::DevNet& net, const PState* states, const uint32_t* list, const uint32_t* count_dev,
                             uint32_t max_n, float* out, int stride, float* logits_out, cudaStream_t stream) {
-  static int sm_count = 0;
-  static bool attr_set = false;
-  if (!attr_set) {
-    int dev = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_eval_umma<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<G>::TOTAL);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
+  // per device (one process may drive one engine per GPU from several host threads): SM count + opt-in shared memory
+  static std::mutex mu;
+  static int sm_counts[64] = {};
+  int dev = 0, sm_count = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    if (sm_counts[dev] == 0) {
+      int n = 0;
+      e = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(k_eval_umma<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<G>::TOTAL);
+      if (e != cudaSuccess) return e;
+      sm_counts[dev] = n;
+    }
+    sm_count = sm_counts[dev];
   }
   const unsigned grid = (unsigned)std::max(1, std::min<int>(sm_count, (int)max_n));
   k_eval_umma<G><<<grid, THREADS, Smem<G>::TOTAL, stream>>>(reinterpret_cast<const uint8_t*>(net.w_umma), states, list, count_dev, max_n,

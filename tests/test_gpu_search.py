@@ -255,3 +255,22 @@ def test_selfplay_step_temperature_sampling_distribution():
         again = [e.get_state(s, 0).key() for s in range(64)]
         e.reset_games(); e.search(sims); e.selfplay_step(S.MOVE_TEMPERATURE, temperature=temp, seed=12345)
         assert again == [e.get_state(s, 0).key() for s in range(64)]
+
+
+def test_one_process_can_drive_engines_on_several_gpus():
+    """main.rs:169 runs one Mcts per worker thread; a host that owns several GPUs creates one engine per device in the
+    same process.  Each engine (tree kernels + tcgen05 evaluator) must work on its own device."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from selfplay_b200.weights_init import random_checkpoint
+    blob = random_checkpoint(1, 0)
+    res = []
+    for dev in (0, 1):
+        with S.Engine(game=S.GAME_C4, num_games=40, evaluator=S.EVAL_NET, device=dev) as e:
+            e.load_weights(blob)
+            e.reset_games()
+            e.search(60)
+            res.append([e.root_children(s) for s in range(40)])
+    assert res[0] == res[1]
+    assert sum(res[0][0][1]) == 59
