@@ -166,6 +166,10 @@ bool Evaluator::upload(const HostNet& net, std::string* err) {
   umma_v1::pack_weights(net, &umma1);
   const size_t off_umma1 = reserve(umma1.size());
   std::memcpy(blob.data() + off_umma1, umma1.data(), umma1.size());
+  std::vector<uint8_t> umma2;
+  umma_v2::pack_weights(net, &umma2);
+  const size_t off_umma2 = reserve(umma2.size());
+  std::memcpy(blob.data() + off_umma2, umma2.data(), umma2.size());
 
   if (d_blob_) { cudaFree(d_blob_); d_blob_ = nullptr; }
   cudaError_t e = cudaMalloc(&d_blob_, blob.size());
@@ -183,6 +187,7 @@ bool Evaluator::upload(const HostNet& net, std::string* err) {
   dev_.vfc_b = reinterpret_cast<const float*>(d + off_vb);
   dev_.w_umma = reinterpret_cast<const uint16_t*>(d + off_umma);
   dev_.w_umma_v1 = reinterpret_cast<const uint16_t*>(d + off_umma1);
+  dev_.w_umma_v2 = reinterpret_cast<const uint16_t*>(d + off_umma2);
   dev_.rows = net.rows; dev_.cols = net.cols; dev_.actions = A;
   game_ = net.game; rows_ = net.rows; cols_ = net.cols; actions_ = A;
   (void)P;
@@ -200,6 +205,11 @@ cudaError_t Evaluator::launch(const PState* states, const uint32_t* list, const 
     else
       k_eval_simt<TicTacToe><<<grid, 256, 0, stream>>>(dev_, states, list, count_dev, max_n, out, stride, logits_out);
     return cudaGetLastError();
+  }
+  if (use_pair_) {
+    DevNet v2 = dev_;
+    v2.w_umma = dev_.w_umma_v2;
+    return umma_v2::launch(v2, game_, states, list, count_dev, max_n, out, stride, logits_out, stream);
   }
   if (use_v1_) {
     DevNet v1 = dev_;

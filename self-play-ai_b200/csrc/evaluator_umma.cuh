@@ -23,4 +23,11 @@ cudaError_t launch(const Evaluator::DevNet& net, int game, const PState* states,
                    const uint32_t* count_dev, uint32_t max_n, float* out, int stride, float* logits_out,
                    cudaStream_t stream);
 }  // namespace umma_v1
+
+namespace umma_v2 {   // kx-pair variant: centre + right taps share one A fetch (N = 128), see evaluator_umma_v2.cu
+void pack_weights(const HostNet& net, std::vector<uint8_t>* out);
+cudaError_t launch(const Evaluator::DevNet& net, int game, const PState* states, const uint32_t* list,
+                   const uint32_t* count_dev, uint32_t max_n, float* out, int stride, float* logits_out,
+                   cudaStream_t stream);
+}  // namespace umma_v2
 }  // namespace spb

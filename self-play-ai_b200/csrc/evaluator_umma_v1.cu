@@ -150,6 +150,16 @@ __device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
     __nanosleep(200);
   }
 }
+template <int NS>
+__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity) {   // waiters with slack: poll less, leave the
+  uint32_t ok;                                                                         // shared-memory pipe to the tensor core
+  for (;;) {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (ok) break;
+    if (NS > 0) __nanosleep(NS);
+  }
+}
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory"); }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
@@ -340,7 +350,12 @@ k_eval_umma(const uint8_t* __restrict__ image, const PState* __restrict__ states
           const uint32_t bytes = (uint32_t)layer_tap_bytes(l);
           const uint8_t* src = image + layer_offset(l);
           for (int s = 0; s < N_SLOTS; ++s) {
+#ifdef V_PROD_SLEEP
+            if (use > 0) mbar_wait_backoff<V_PROD_SLEEP>(bar_w_empty(s), (use - 1) & 1u);
+#else
             if (use > 0) mbar_wait(bar_w_empty(s), (use - 1) & 1u);
+#endif
+            if (DBG(4) && use > 0) { mbar_arrive(bar_w_full(s)); continue; }   // profile build: no weight traffic
             mbar_expect_tx(bar_w_full(s), bytes);
             bulk_g2s(s_base + Sm::OFF_W + (uint32_t)s * SLOT_BYTES, src + (size_t)s * bytes, bytes, bar_w_full(s));
           }
@@ -379,6 +394,7 @@ k_eval_umma(const uint8_t* __restrict__ image, const PState* __restrict__ states
 #ifdef SPB_PROFILE
             if (lane == 0) g_eval_prof_layer[blockIdx.x][l] += clock64() - prof_t0;
             const unsigned long long w_before = prof_w;
+            prof_t0 = clock64();
 #endif
             tc_fence_after();
             const uint32_t a_lo_tile = a_lo_base + (uint32_t)t * 128u;
@@ -391,7 +407,14 @@ k_eval_umma(const uint8_t* __restrict__ image, const PState* __restrict__ states
             else
               issue_tile<Ge::W8, Ge::Q, 4, HEAD_N>(issuer, a_lo_tile, b_lo_base, SLOT_BYTES >> 4, d_tmem, first, last, use & 1u, bar_base, prof_w);
 #ifdef SPB_PROFILE
-            if (lane == 0) g_eval_prof_layer[blockIdx.x][10 + l] += prof_w - w_before;
+            if (lane == 0) {
+              g_eval_prof_layer[blockIdx.x][10 + l] += prof_w - w_before;
+              if (l >= 1 && l <= 8 && nt == 4) {   // issue time of one residual-layer tile by position, weight waits excluded
+                const unsigned long long dt = clock64() - prof_t0 - (prof_w - w_before);
+                g_eval_prof_layer[blockIdx.x][20 + (first ? 0 : last ? 2 : 1)] += dt;
+                if (first) g_eval_prof_layer[blockIdx.x][23] += 1;
+              }
+            }
 #endif
             if (issuer) umma_commit(bar_acc_full(b & 1u, t));
             __syncwarp();
@@ -490,17 +513,29 @@ k_eval_umma(const uint8_t* __restrict__ image, const PState* __restrict__ states
             uint4 sk[4];
             if (has_skip) {                                         // (x + f(x)).relu(), model/mod.rs:163
 #pragma unroll
-              for (int j = 0; j < 4; ++j) sk[j] = *reinterpret_cast<const uint4*>(drow + (size_t)j * Ge::Q * 16);
+              for (int j = 0; j < 4; ++j) sk[j] = DBG(2) ? make_uint4(0, 0, 0, 0) : *reinterpret_cast<const uint4*>(drow + (size_t)j * Ge::Q * 16);
             }
             PROF_BEGIN();
+#ifdef V_EPI_BACKOFF
+            mbar_wait_backoff<V_EPI_BACKOFF>(bar_acc_full(b & 1u, t), (cur_par >> t) & 1u);
+#else
             mbar_wait(bar_acc_full(b & 1u, t), (cur_par >> t) & 1u);
+#endif
             PROF_END(prof_acc0);
             tc_fence_after();
+#ifdef SPB_PROFILE
+            const unsigned long long body0 = clock64();
+#endif
             const uint32_t taddr = tmem_acc + ((uint32_t)(quad * 32) << 16) + (uint32_t)t * 64u + (uint32_t)half * 32u;
             uint32_t a[32];
-            tmem_ld16(taddr, a);
-            tmem_ld16(taddr + 16, a + 16);
-            tmem_ld_wait();
+            if (DBG(0)) {
+#pragma unroll
+              for (int q = 0; q < 32; ++q) a[q] = 0;
+            } else {
+              tmem_ld16(taddr, a);
+              tmem_ld16(taddr + 16, a + 16);
+              tmem_ld_wait();
+            }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {                           // one 8-channel chunk = one 16-B store
               float v[8];
@@ -517,11 +552,15 @@ k_eval_umma(const uint8_t* __restrict__ image, const PState* __restrict__ states
                 o.z = pack_bf16x2(fmaxf(v[4], 0.f), fmaxf(v[5], 0.f));
                 o.w = pack_bf16x2(fmaxf(v[6], 0.f), fmaxf(v[7], 0.f));
               }
-              *reinterpret_cast<uint4*>(drow + (size_t)j * Ge::Q * 16) = o;
+              if (!DBG(1)) *reinterpret_cast<uint4*>(drow + (size_t)j * Ge::Q * 16) = o;
             }
             fence_async_smem();
             tc_fence_before();
             mbar_arrive(bar_act_ready(t));
+#ifdef SPB_PROFILE
+            prof_acc1 += clock64() - body0;
+            prof_acc2 += 1;
+#endif
           }
         } else {
           // The head conv's MMAs are in flight: stage the next batch now (buffer 0 is no longer read by this batch).
@@ -639,6 +678,8 @@ k_eval_umma(const uint8_t* __restrict__ image, const PState* __restrict__ states
     if (et == 0) {
       g_eval_prof[blockIdx.x][3] = clock64() - prof_start;     // epilogue warp total
       g_eval_prof[blockIdx.x][4] = prof_acc0;                  // waiting for accumulators (MMA)
+      g_eval_prof[blockIdx.x][6] = prof_acc1;                  // conv-layer epilogue bodies (after the wait, through the arrive)
+      g_eval_prof[blockIdx.x][7] = prof_acc2;                  // number of such bodies
     }
 #endif
   }

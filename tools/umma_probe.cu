@@ -144,6 +144,25 @@ __global__ void __launch_bounds__(128) probe(Params p, const __nv_bfloat16* gA, 
     long long t2 = clock64();
     if (blockIdx.x == 0) { gcycles[0] = t1 - t0; gcycles[1] = t2 - t0; }
   }
+  // T5: how far can the issuing thread run ahead of the tensor pipe?  Time stamp after each of 40 back-to-back issues.
+  if (p.iters < 0 && tid == 0) {
+    uint64_t ad = make_desc(smem_u32(sA) + 16 * 16, a_lbo, a_sbo);
+    uint64_t bd = make_desc(smem_u32(sB), b_lbo, b_sbo);
+    long long ts[41];
+    ts[0] = clock64();
+#pragma unroll
+    for (int i = 0; i < 40; ++i) {
+      umma_f16(tmem, ad, bd, idesc, 1);
+      ts[i + 1] = clock64();
+    }
+    umma_commit(smem_u32(&bar));
+    mbar_wait(smem_u32(&bar), parity);
+    long long t2 = clock64();
+    if (blockIdx.x == 0) {
+      for (int i = 0; i <= 40; ++i) gcycles[i] = ts[i] - ts[0];
+      gcycles[41] = t2 - ts[0];
+    }
+  }
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
@@ -238,6 +257,18 @@ int main() {
   for (int N : {16, 32, 48, 64, 128, 256}) { if (N > NMAX) continue;
     run({N, 0, swap, 64, 0}, "T3 timing same-A");
     run({N, 0, swap, 64, 1}, "T3 timing shifted taps");
+  }
+  // T5
+  for (int N : {64, 256}) { if (N > NMAX) continue;
+    Params p{N, 0, swap, -1, 0};
+    CK(cudaMemset(dC, 0, 64 * 8));
+    probe<<<1, 128, smem_bytes>>>(p, dA, dB, dD, dC);
+    CK(cudaDeviceSynchronize());
+    long long c[42];
+    CK(cudaMemcpy(c, dC, sizeof c, cudaMemcpyDeviceToHost));
+    printf("T5 issue-queue depth N=%3d: cycles at which MMA i had been issued (i=1..40):", N);
+    for (int i = 1; i <= 40; ++i) printf(" %lld", c[i]);
+    printf(" | all complete at %lld\n", c[41]);
   }
   // T4
   uint8_t* dsrc;
