@@ -177,8 +177,11 @@ def run_ours(args):
 
     G, sims = args.games, args.sims
     blob = random_checkpoint(1, 0)
+    # node pools sized for the full-game leg (a tree can carry nearly all of its nodes through a re-root and adds at most
+    # 7 per simulation), so that no pool growth (spb_search widens the pools on demand) lands inside a timed region
     eng = S.Engine(game=S.GAME_C4, num_games=G, evaluator=S.EVAL_NET, device=local_rank,
-                   game_id_base=rank * G, game_id_stride=world * G)
+                   game_id_base=rank * G, game_id_stride=world * G,
+                   max_nodes_per_tree=1024 * ((7 * sims * (args.full_game_moves + 1) + 1024) // 1024))
     eng.load_weights(blob)
     roots = synthetic_roots_device(eng, G, start=rank * G)       # games are sharded by rank: rank r owns ids [r*G, (r+1)*G)
 
@@ -257,7 +260,7 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
-                     "traffic": 813568, "kernel": "k_eval_umma<Connect4>", "peak_source": peak_src,
+                     "traffic": 849152, "kernel": "umma_v2::k_eval_umma<Connect4>", "peak_source": peak_src,
                      "positions_per_launch": n_pos, "flops_per_position": flops_pos, "avg_launch_ms": eval_ms},
         "roofline_tree": {"bound": "hbm", "unit": "GB/s", "peak": peak_hbm, "bytes_per_sim": tree_bytes_per_sim, "mean_path_length": D,
                           "mean_branching": bbar, "tree_us_per_step": tree_us,
@@ -292,8 +295,10 @@ def run_ours(args):
         line["cpu_baseline"] = None
     # ---- multi-GPU: the one exchange of the path — trajectories to the learner rank -------------------
     if world > 1:
-        from selfplay_b200.distributed import gather_trajectories
+        from selfplay_b200.distributed import gather_records, gather_trajectories
         eng.selfplay_step(S.MOVE_GREEDY_LAST_MAX)
+        gather_records(np.zeros(0, S.POSITION_DTYPE), np.zeros(0, np.uint64), dst=0)   # NCCL sets up its gather connections on first use
+        barrier()
         t0 = time.perf_counter()
         pos, gids = gather_trajectories(eng, dst=0)
         line["trajectory_gather"] = {"positions": int(len(pos)) if rank == 0 else None, "seconds": time.perf_counter() - t0}

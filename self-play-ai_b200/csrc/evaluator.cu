@@ -158,10 +158,6 @@ bool Evaluator::upload(const HostNet& net, std::string* err) {
   std::memcpy(blob.data() + off_vw, net.vfc_w.data(), net.vfc_w.size() * 4);
   std::memcpy(blob.data() + off_vb, net.vfc_b.data(), net.vfc_b.size() * 4);
   // tcgen05 operand images + epilogue tables
-  std::vector<uint8_t> umma;
-  umma::pack_weights(net, &umma);
-  const size_t off_umma = reserve(umma.size());
-  std::memcpy(blob.data() + off_umma, umma.data(), umma.size());
   std::vector<uint8_t> umma1;
   umma_v1::pack_weights(net, &umma1);
   const size_t off_umma1 = reserve(umma1.size());
@@ -185,7 +181,7 @@ bool Evaluator::upload(const HostNet& net, std::string* err) {
   dev_.pfc_b = reinterpret_cast<const float*>(d + off_pb);
   dev_.vfc_w = reinterpret_cast<const float*>(d + off_vw);
   dev_.vfc_b = reinterpret_cast<const float*>(d + off_vb);
-  dev_.w_umma = reinterpret_cast<const uint16_t*>(d + off_umma);
+  dev_.w_umma = nullptr;
   dev_.w_umma_v1 = reinterpret_cast<const uint16_t*>(d + off_umma1);
   dev_.w_umma_v2 = reinterpret_cast<const uint16_t*>(d + off_umma2);
   dev_.rows = net.rows; dev_.cols = net.cols; dev_.actions = A;
@@ -206,17 +202,13 @@ cudaError_t Evaluator::launch(const PState* states, const uint32_t* list, const 
       k_eval_simt<TicTacToe><<<grid, 256, 0, stream>>>(dev_, states, list, count_dev, max_n, out, stride, logits_out);
     return cudaGetLastError();
   }
-  if (use_pair_) {
-    DevNet v2 = dev_;
-    v2.w_umma = dev_.w_umma_v2;
-    return umma_v2::launch(v2, game_, states, list, count_dev, max_n, out, stride, logits_out, stream);
-  }
+  DevNet net = dev_;
   if (use_v1_) {
-    DevNet v1 = dev_;
-    v1.w_umma = dev_.w_umma_v1;
-    return umma_v1::launch(v1, game_, states, list, count_dev, max_n, out, stride, logits_out, stream);
+    net.w_umma = dev_.w_umma_v1;
+    return umma_v1::launch(net, game_, states, list, count_dev, max_n, out, stride, logits_out, stream);
   }
-  return umma::launch(dev_, game_, states, list, count_dev, max_n, out, stride, logits_out, stream);
+  net.w_umma = dev_.w_umma_v2;
+  return umma_v2::launch(net, game_, states, list, count_dev, max_n, out, stride, logits_out, stream);
 }
 
 }  // namespace spb

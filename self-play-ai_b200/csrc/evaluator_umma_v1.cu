@@ -1,5 +1,5 @@
 // evaluator_umma_v1.cu — the fused policy/value network on tcgen05 tensor cores (sm_100a): one MMA group per 3x3 tap (N = 64).
-// This is the DEFAULT evaluator kernel.  evaluator_umma.cu holds the experimental dx-sharing variant (SPB_FLAG_EVAL_DX).
+// This is the FIRST tcgen05 evaluator, kept as a cross-check (SPB_FLAG_EVAL_V1).  The default is evaluator_umma_v2.cu.
 //
 // Replaces Net::forward + softmax of the reference (ref: src/model/connect_four.rs:75-81,
 // src/model/tictactoe.rs:75-81, src/model/mod.rs:62-63; layers model/mod.rs:152-184,

@@ -46,8 +46,9 @@ def test_tcgen05_evaluator_matches_torch(game, n):
 
 @pytest.mark.parametrize("game", [S.GAME_C4, S.GAME_TTT], ids=["c4", "ttt"])
 @pytest.mark.parametrize("n", [1, 19, 2000])
-def test_tcgen05_dx_sharing_variant_matches_torch(game, n):
-    _check(game, S.FLAG_EVAL_DX, n, 2, torch_net.to_safetensors_tch)
+def test_first_tcgen05_kernel_matches_torch(game, n):
+    """SPB_FLAG_EVAL_V1: one MMA group per tap (N = 64), kept as a cross-check of the default kx-pair kernel."""
+    _check(game, S.FLAG_EVAL_V1, n, 2, torch_net.to_safetensors_tch)
 
 
 def test_tcgen05_and_simt_agree_closely():

@@ -1,4 +1,4 @@
-"""Correctness + timing of the kx-pair evaluator (SPB_FLAG_EVAL_PAIR) against the default kernel and torch."""
+"""Correctness + timing of the kx-pair evaluator (default) against the first tcgen05 kernel (SPB_FLAG_EVAL_V1) and the SIMT kernel."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
@@ -10,7 +10,7 @@ from selfplay_b200.weights_init import random_checkpoint
 for game, tag in ((S.GAME_C4, "c4"), (S.GAME_TTT, "ttt")):
     blob = random_checkpoint(game, 0)
     outs = {}
-    for flags, name in ((0, "v1"), (S.FLAG_EVAL_PAIR, "pair"), (S.FLAG_EVAL_SIMT, "simt")):
+    for flags, name in ((S.FLAG_EVAL_V1, "v1"), (0, "pair"), (S.FLAG_EVAL_SIMT, "simt")):
         with S.Engine(game=game, num_games=64, evaluator=S.EVAL_NET, flags=flags) as e:
             e.load_weights(blob)
             roots = synthetic_roots_device(e, 700, max_ply=21 if game == S.GAME_C4 else 5)
@@ -22,7 +22,7 @@ for game, tag in ((S.GAME_C4, "c4"), (S.GAME_TTT, "ttt")):
         print("%s %s vs v1: max |dlogit| %.3e (scale %.3f)  max |dvalue| %.3e" % (tag, name, dl, np.abs(outs["v1"][2]).max(), dv), flush=True)
 
 G, sims = 4096, 200
-for flags, name in ((0, "v1"), (S.FLAG_EVAL_PAIR, "pair")):
+for flags, name in ((S.FLAG_EVAL_V1, "v1"), (0, "pair")):
     with S.Engine(game=S.GAME_C4, num_games=G, evaluator=S.EVAL_NET, flags=flags) as e:
         e.load_weights(random_checkpoint(1, 0))
         roots = synthetic_roots_device(e, G)

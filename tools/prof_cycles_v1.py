@@ -8,10 +8,10 @@ if os.environ.get("SPB_LIB"):
 import selfplay_b200 as S
 from selfplay_b200.synth import synthetic_roots_device
 from selfplay_b200.weights_init import random_checkpoint
-VER = os.environ.get("SPB_VER", "v1")
+VER = os.environ.get("SPB_VER", "v2")
 G = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 sims = int(sys.argv[2]) if len(sys.argv) > 2 else 40
-with S.Engine(game=S.GAME_C4, num_games=G, evaluator=S.EVAL_NET, flags=S.FLAG_NO_GRAPH | (S.FLAG_EVAL_PAIR if os.environ.get("SPB_VER", "v1") == "v2" else 0)) as e:
+with S.Engine(game=S.GAME_C4, num_games=G, evaluator=S.EVAL_NET, flags=S.FLAG_NO_GRAPH | (S.FLAG_EVAL_V1 if os.environ.get("SPB_VER", "v2") == "v1" else 0)) as e:
     e.load_weights(random_checkpoint(1, 0))
     roots = synthetic_roots_device(e, G)
     e.reset_games(roots)
