@@ -98,6 +98,7 @@ typedef struct spb_config {
 #define SPB_FLAG_EVAL_SIMT  2u   /* use the CUDA-core evaluator kernel instead of tcgen05 (debug / cross-check) */
 #define SPB_FLAG_EVAL_V1    32u  /* use the first tcgen05 evaluator kernel (one MMA group per 3x3 tap, N = 64) instead of the default
                                     kx-pair kernel (centre + right taps share one A fetch, N = 128): cross-check / A-B timing */
+#define SPB_FLAG_EVAL_PAIR2 64u  /* tcgen05 evaluator on CTA pairs (cta_group::2): experimental */
 #define SPB_FLAG_FIXED_POOL 16u  /* never grow the node pools: a tree that would pass max_nodes_per_tree makes spb_search return
                                     SPB_ERR_POOL.  Without the flag the pools grow before a search that could outgrow them, like
                                     the reference's Vec arena (mcts.rs:19) */

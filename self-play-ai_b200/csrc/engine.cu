@@ -948,6 +948,7 @@ int32_t spb_create(const spb_config* cfg, spb_engine** out) {
   spb_engine* e = new (std::nothrow) spb_engine();
   if (!e) { g_create_error = "out of host memory"; return SPB_ERR_NOMEM; }
   e->cfg = *cfg;
+  e->evaluator.use_v3((cfg->flags & SPB_FLAG_EVAL_PAIR2) != 0);
   e->evaluator.use_v1((cfg->flags & SPB_FLAG_EVAL_V1) != 0);   // default: kx-pair kernel (evaluator_umma_v2.cu)
   if (e->cfg.max_nodes_per_tree == 0) e->cfg.max_nodes_per_tree = 16384;
   if (e->cfg.max_nodes_per_tree < 16 || e->cfg.max_nodes_per_tree > MAX_CAP) { g_create_error = "max_nodes_per_tree out of range"; delete e; return SPB_ERR_ARG; }

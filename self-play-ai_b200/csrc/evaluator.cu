@@ -162,6 +162,10 @@ bool Evaluator::upload(const HostNet& net, std::string* err) {
   umma_v1::pack_weights(net, &umma1);
   const size_t off_umma1 = reserve(umma1.size());
   std::memcpy(blob.data() + off_umma1, umma1.data(), umma1.size());
+  std::vector<uint8_t> umma3;
+  umma_v3::pack_weights(net, &umma3);
+  const size_t off_umma3 = reserve(umma3.size());
+  std::memcpy(blob.data() + off_umma3, umma3.data(), umma3.size());
   std::vector<uint8_t> umma2;
   umma_v2::pack_weights(net, &umma2);
   const size_t off_umma2 = reserve(umma2.size());
@@ -184,6 +188,7 @@ bool Evaluator::upload(const HostNet& net, std::string* err) {
   dev_.w_umma = nullptr;
   dev_.w_umma_v1 = reinterpret_cast<const uint16_t*>(d + off_umma1);
   dev_.w_umma_v2 = reinterpret_cast<const uint16_t*>(d + off_umma2);
+  dev_.w_umma_v3 = reinterpret_cast<const uint16_t*>(d + off_umma3);
   dev_.rows = net.rows; dev_.cols = net.cols; dev_.actions = A;
   game_ = net.game; rows_ = net.rows; cols_ = net.cols; actions_ = A;
   (void)P;
@@ -206,6 +211,10 @@ cudaError_t Evaluator::launch(const PState* states, const uint32_t* list, const 
   if (use_v1_) {
     net.w_umma = dev_.w_umma_v1;
     return umma_v1::launch(net, game_, states, list, count_dev, max_n, out, stride, logits_out, stream);
+  }
+  if (use_v3_) {
+    net.w_umma = dev_.w_umma_v3;
+    return umma_v3::launch(net, game_, states, list, count_dev, max_n, out, stride, logits_out, stream);
   }
   net.w_umma = dev_.w_umma_v2;
   return umma_v2::launch(net, game_, states, list, count_dev, max_n, out, stride, logits_out, stream);

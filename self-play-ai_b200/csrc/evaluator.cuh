@@ -43,6 +43,7 @@ class Evaluator {
   // Uploads the folded net: bf16 conv weights in the tcgen05 shared-memory layout + f32 biases / FCs.
   bool upload(const HostNet& net, std::string* err);
   bool loaded() const { return loaded_; }
+  void use_v3(bool v) { use_v3_ = v; }   // CTA-pair kernel (evaluator_umma_v3.cu)
   void use_v1(bool v) { use_v1_ = v; }   // true = first tcgen05 kernel (one MMA group per tap, SPB_FLAG_EVAL_V1); default = kx-pair kernel
   int game() const { return game_; }
 
@@ -59,6 +60,7 @@ class Evaluator {
  private:
   bool loaded_ = false;
   bool use_v1_ = false;
+  bool use_v3_ = false;
   int game_ = -1, rows_ = 0, cols_ = 0, actions_ = 0;
   void* d_blob_ = nullptr;      // one allocation holding everything below
   size_t blob_bytes_ = 0;
@@ -69,6 +71,7 @@ class Evaluator {
     const float* bias[NET_CONVS];        // f32 [OC]
     const uint16_t* w_umma;              // image the launched tcgen05 kernel reads (set per launch to one of the two below)
     const uint16_t* w_umma_v1;           // image of the first kernel (one MMA group per tap, evaluator_umma_v1.cu)
+    const uint16_t* w_umma_v3;           // image of the CTA-pair kernel (evaluator_umma_v3.cu)
     const uint16_t* w_umma_v2;           // image of the default kx-pair kernel (evaluator_umma_v2.cu)
     const float* pfc_w; const float* pfc_b; const float* vfc_w; const float* vfc_b;
     int rows, cols, actions;

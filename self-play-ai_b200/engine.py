@@ -16,7 +16,7 @@ ONGOING, TIED, WON = 0, 1, 2
 MAX_ACTIONS = 9
 NUM_ACTIONS = {GAME_TTT: 9, GAME_C4: 7}
 BOARD = {GAME_TTT: (3, 3), GAME_C4: (6, 7)}
-FLAG_NO_GRAPH, FLAG_EVAL_SIMT, FLAG_FORCE_SPLIT, FLAG_FIXED_POOL, FLAG_EVAL_V1 = 1, 2, 4, 16, 32
+FLAG_NO_GRAPH, FLAG_EVAL_SIMT, FLAG_FORCE_SPLIT, FLAG_FIXED_POOL, FLAG_EVAL_V1, FLAG_EVAL_PAIR2 = 1, 2, 4, 16, 32, 64
 MOVE_GREEDY_LAST_MAX, MOVE_TEMPERATURE = 0, 1
 ABI_VERSION = 1
 

@@ -51,6 +51,23 @@ def test_first_tcgen05_kernel_matches_torch(game, n):
     _check(game, S.FLAG_EVAL_V1, n, 2, torch_net.to_safetensors_tch)
 
 
+@pytest.mark.parametrize("game", [S.GAME_C4, S.GAME_TTT], ids=["c4", "ttt"])
+@pytest.mark.parametrize("n", [1, 2, 19, 37, 2000])
+def test_cta_pair_kernel_is_bit_identical_to_the_default(game, n):
+    """SPB_FLAG_EVAL_PAIR2 (tcgen05 cta_group::2: two CTAs share every B operand) performs the same arithmetic in the same
+    order as the default kernel: identical logits, values and policies for every batch shape (odd counts leave the peer
+    CTA of a pair with fewer or no boards)."""
+    net = torch_net.make_net(game, seed=5)
+    states = random_states(game, n, seed=11, include_terminal=False)
+    outs = []
+    for flags in (0, S.FLAG_EVAL_PAIR2):
+        with S.Engine(game=game, num_games=4, evaluator=S.EVAL_NET, flags=flags) as e:
+            e.load_weights(torch_net.to_safetensors_tch(net))
+            outs.append(e.predict(states, want_logits=True))
+    for a, b in zip(outs[0], outs[1]):
+        assert np.array_equal(a, b)
+
+
 def test_tcgen05_and_simt_agree_closely():
     lg0, v0 = _check(S.GAME_C4, 0, 257, 4, torch_net.to_safetensors_explicit)
     lg1, v1 = _check(S.GAME_C4, S.FLAG_EVAL_SIMT, 257, 4, torch_net.to_safetensors_explicit)

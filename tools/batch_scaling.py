@@ -8,7 +8,7 @@ import selfplay_b200 as S
 from selfplay_b200.synth import synthetic_roots_device
 from selfplay_b200.weights_init import random_checkpoint
 blob = random_checkpoint(1, 0)
-for name, flags in (("v1", S.FLAG_EVAL_V1), ("pair (default)", 0)):
+for name, flags in (("pair (default)", 0), ("pair2", S.FLAG_EVAL_PAIR2)):
     res = []
     for n in (148 * 2, 148 * 4, 148 * 9, 148 * 11, 148 * 13, 148 * 18, 148 * 21, 148 * 27, 148 * 36, 148 * 72):
         with S.Engine(game=S.GAME_C4, num_games=n, evaluator=S.EVAL_NET, flags=flags | S.FLAG_NO_GRAPH) as e:

@@ -10,16 +10,17 @@ import selfplay_b200 as S
 from selfplay_b200.synth import synthetic_roots_device
 from selfplay_b200.weights_init import random_checkpoint
 G = 4096
-with S.Engine(game=S.GAME_C4, num_games=G, evaluator=S.EVAL_NET, flags=S.FLAG_NO_GRAPH) as e:
+VER = os.environ.get("SPB_VER", "v2")
+with S.Engine(game=S.GAME_C4, num_games=G, evaluator=S.EVAL_NET, flags=S.FLAG_NO_GRAPH | (S.FLAG_EVAL_PAIR2 if VER == "v3" else 0)) as e:
     e.load_weights(random_checkpoint(1, 0))
     roots = synthetic_roots_device(e, G)
     e.reset_games(roots)
     e.search(60)
     L = S.load_library()
     tr = np.zeros((4, 512), np.uint64)
-    L.spb_debug_trace_v2(C.c_void_p(tr.ctypes.data), 1)
+    getattr(L, "spb_debug_trace_" + VER)(C.c_void_p(tr.ctypes.data), 1)
     ms, n, fl = e.time_evaluator(3)
-    L.spb_debug_trace_v2(C.c_void_p(tr.ctypes.data), 0)
+    getattr(L, "spb_debug_trace_" + VER)(C.c_void_p(tr.ctypes.data), 0)
     tr = tr.astype(np.int64)
     t0 = tr[0][tr[0] > 0].min()
     print("evaluator %.1f us, %d positions; times in cycles from the first MMA issue of CTA 0" % (ms * 1e3, n))
