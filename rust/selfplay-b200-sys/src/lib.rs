@@ -25,6 +25,7 @@ pub const SPB_FLAG_NO_GRAPH: u32 = 1;
 pub const SPB_FLAG_EVAL_SIMT: u32 = 2;
 pub const SPB_FLAG_FORCE_SPLIT: u32 = 4;
 pub const SPB_FLAG_EVAL_V1: u32 = 32;
+pub const SPB_FLAG_EVAL_PAIR2: u32 = 64;
 pub const SPB_FLAG_FIXED_POOL: u32 = 16;
 pub const SPB_MOVE_GREEDY_LAST_MAX: i32 = 0;
 pub const SPB_MOVE_TEMPERATURE: i32 = 1;

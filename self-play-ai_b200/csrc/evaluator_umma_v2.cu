@@ -220,11 +220,10 @@ __device__ __forceinline__ float bf_hi(uint32_t u) { return __uint_as_float(u & 
 template <int W8, int Q, int KSTEPS, int N>
 __device__ __forceinline__ void issue_tile(bool issuer, uint32_t a_lo_tile, uint32_t b_lo_base, uint32_t slot_stride16,
                                            uint32_t d_tmem, bool first_tile, bool last_tile, uint32_t w_par, uint32_t bar_base,
-                                           uint32_t mid_bar, uint32_t mid_par, unsigned long long& prof_wfull) {
+                                           uint32_t mid_bar, uint32_t mid_par) {
   constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);          // SBO = 128 B, descriptor version 1
   constexpr uint32_t IDESC = make_idesc(N);
   (void)slot_stride16;
-  (void)prof_wfull;
 #pragma unroll
   for (int tap = 0; tap < 9; ++tap) {
     if (tap == 6 && mid_bar) {                                    // the bottom kernel row reads the first rows of the next tile
@@ -257,10 +256,9 @@ __device__ __forceinline__ void issue_tile(bool issuer, uint32_t a_lo_tile, uint
 template <int W8, int Q>
 __device__ __forceinline__ void issue_tile_pair(bool issuer, uint32_t a_lo_tile, uint32_t b_lo_base, uint32_t d_tmem,
                                                 bool first_tile, bool last_tile, uint32_t w_par, uint32_t bar_base,
-                                                uint32_t mid_bar, uint32_t mid_par, unsigned long long& prof_wfull) {
+                                                uint32_t mid_bar, uint32_t mid_par) {
   constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);
   constexpr uint32_t IDESC128 = make_idesc(128), IDESC64 = make_idesc(64);
-  (void)prof_wfull;
 #pragma unroll
   for (int ky = 0; ky < 3; ++ky) {
     const int shift = (ky - 1) * W8;
@@ -325,21 +323,6 @@ __device__ unsigned long long g_trace[4][512];   // [0] MMA issue begin, [1] MMA
 #else
 #define TRACE2(i) ((void)0)
 #define TRACE(k, b, l, t) ((void)0)
-#endif
-#ifdef SPB_PROFILE
-// debug build only (make PROFILE=1): per-CTA cycle attribution
-__device__ unsigned long long g_eval_prof[160][8];
-__device__ unsigned long long g_eval_prof_layer[160][24];   // [cta][0..9] act waits per layer, [10..19] weight waits per layer
-__device__ int g_eval_debug = 0;   // bit0: epilogue skips tcgen05.ld, bit1: skips st.shared, bit2: skips skip-loads, bit3: no per-tap commits
-#define DBG(bit) (g_eval_debug & (1 << (bit)))
-#define PROF_DECL unsigned long long prof_t0 = 0, prof_acc0 = 0, prof_acc1 = 0, prof_acc2 = 0;
-#define PROF_BEGIN() (prof_t0 = clock64())
-#define PROF_END(acc) ((acc) += clock64() - prof_t0)
-#else
-#define DBG(bit) 0
-#define PROF_DECL
-#define PROF_BEGIN() ((void)0)
-#define PROF_END(acc) ((void)0)
 #endif
 
 template <class G>
@@ -420,11 +403,6 @@ k_eval_umma(const uint8_t* __restrict__ image, const PState* __restrict__ states
     // The whole warp runs the (warp-uniform) control flow so that descriptors stay in uniform registers;
     // one fixed lane issues the tcgen05 instructions.
     {
-      PROF_DECL
-#ifdef SPB_PROFILE
-      const unsigned long long prof_start = clock64();
-#endif
-      unsigned long long prof_w = 0;
       const bool issuer = elect_one();
       const uint32_t b_lo_base = ((s_base + Sm::OFF_W) >> 4);
       uint32_t use = 0;        // layer-uses of the weight ring so far
@@ -459,11 +437,11 @@ k_eval_umma(const uint8_t* __restrict__ image, const PState* __restrict__ states
             const uint32_t d_tmem = tmem_base + (uint32_t)t * 128u + (l == 0 ? 64u : 0u);
             const bool first = (t == 0), last = (t == nt - 1);
             if (l == 0)
-              issue_tile<Ge::W8, Ge::Q, 1, 64>(issuer, a_lo_tile, b_lo_base, 2048 >> 4, d_tmem, first, last, use & 1u, bar_base, 0u, 0u, prof_w);
+              issue_tile<Ge::W8, Ge::Q, 1, 64>(issuer, a_lo_tile, b_lo_base, 2048 >> 4, d_tmem, first, last, use & 1u, bar_base, 0u, 0u);
             else if (l < 9)
-              issue_tile_pair<Ge::W8, Ge::Q>(issuer, a_lo_tile, b_lo_base, d_tmem, first, last, use & 1u, bar_base, mid_bar, mid_par, prof_w);
+              issue_tile_pair<Ge::W8, Ge::Q>(issuer, a_lo_tile, b_lo_base, d_tmem, first, last, use & 1u, bar_base, mid_bar, mid_par);
             else
-              issue_tile<Ge::W8, Ge::Q, 4, HEAD_N>(issuer, a_lo_tile, b_lo_base, SLOT_BYTES >> 4, d_tmem, first, last, use & 1u, bar_base, mid_bar, mid_par, prof_w);
+              issue_tile<Ge::W8, Ge::Q, 4, HEAD_N>(issuer, a_lo_tile, b_lo_base, SLOT_BYTES >> 4, d_tmem, first, last, use & 1u, bar_base, mid_bar, mid_par);
             if (issuer) {
               umma_commit(bar_acc_full(b & 1u, t));
               if (l == 8 && last) umma_commit(bar_act0_free);
@@ -474,14 +452,6 @@ k_eval_umma(const uint8_t* __restrict__ image, const PState* __restrict__ states
           ++use;
         }
       }
-#ifdef SPB_PROFILE
-      if (lane == 0) {
-        g_eval_prof[blockIdx.x][0] = clock64() - prof_start;   // MMA warp total
-        g_eval_prof[blockIdx.x][1] = prof_acc0;                // waiting for activations (epilogue)
-        g_eval_prof[blockIdx.x][2] = n_batches;
-        g_eval_prof[blockIdx.x][5] = prof_w;                    // waiting for weights (TMA ring)
-      }
-#endif
     }
   } else if (warp == STAGER_WARP) {
     // ===== stager: fetches the states of batch bb and writes their encoding (get_encoding, connect_four.rs:242-259:
@@ -825,17 +795,6 @@ extern "C" int spb_debug_trace_v2(unsigned long long* out, int reset) {
   int rc = (int)cudaMemcpyFromSymbol(out, g_trace, sizeof(unsigned long long) * 4 * 512);
   if (reset) { static unsigned long long z[4 * 512]; rc |= (int)cudaMemcpyToSymbol(g_trace, z, sizeof z); }
   return rc;
-}
-#endif
-#ifdef SPB_PROFILE
-extern "C" int spb_debug_set_v2(int v) { return (int)cudaMemcpyToSymbol(g_eval_debug, &v, sizeof v); }
-extern "C" int spb_debug_eval_profile_layers_v2(unsigned long long* out, int n_ctas, int reset) {
-  int rc = (int)cudaMemcpyFromSymbol(out, g_eval_prof_layer, sizeof(unsigned long long) * 24 * (size_t)n_ctas);
-  if (reset) { static unsigned long long z[160 * 24]; rc |= (int)cudaMemcpyToSymbol(g_eval_prof_layer, z, sizeof z); }
-  return rc;
-}
-extern "C" int spb_debug_eval_profile_v2(unsigned long long* out, int n_ctas) {
-  return (int)cudaMemcpyFromSymbol(out, g_eval_prof, sizeof(unsigned long long) * 8 * (size_t)n_ctas);
 }
 #endif
 

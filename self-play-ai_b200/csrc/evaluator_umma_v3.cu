@@ -383,21 +383,6 @@ __device__ unsigned long long g_trace[4][512];   // [0] MMA issue begin, [1] MMA
 #define TRACE2(i) ((void)0)
 #define TRACE(k, b, l, t) ((void)0)
 #endif
-#ifdef SPB_PROFILE
-// debug build only (make PROFILE=1): per-CTA cycle attribution
-__device__ unsigned long long g_eval_prof[160][8];
-__device__ unsigned long long g_eval_prof_layer[160][24];   // [cta][0..9] act waits per layer, [10..19] weight waits per layer
-__device__ int g_eval_debug = 0;   // bit0: epilogue skips tcgen05.ld, bit1: skips st.shared, bit2: skips skip-loads, bit3: no per-tap commits
-#define DBG(bit) (g_eval_debug & (1 << (bit)))
-#define PROF_DECL unsigned long long prof_t0 = 0, prof_acc0 = 0, prof_acc1 = 0, prof_acc2 = 0;
-#define PROF_BEGIN() (prof_t0 = clock64())
-#define PROF_END(acc) ((acc) += clock64() - prof_t0)
-#else
-#define DBG(bit) 0
-#define PROF_DECL
-#define PROF_BEGIN() ((void)0)
-#define PROF_END(acc) ((void)0)
-#endif
 
 template <class G>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
@@ -894,17 +879,6 @@ extern "C" int spb_debug_trace_v3(unsigned long long* out, int reset) {
   int rc = (int)cudaMemcpyFromSymbol(out, g_trace, sizeof(unsigned long long) * 4 * 512);
   if (reset) { static unsigned long long z[4 * 512]; rc |= (int)cudaMemcpyToSymbol(g_trace, z, sizeof z); }
   return rc;
-}
-#endif
-#ifdef SPB_PROFILE
-extern "C" int spb_debug_set_v3(int v) { return (int)cudaMemcpyToSymbol(g_eval_debug, &v, sizeof v); }
-extern "C" int spb_debug_eval_profile_layers_v3(unsigned long long* out, int n_ctas, int reset) {
-  int rc = (int)cudaMemcpyFromSymbol(out, g_eval_prof_layer, sizeof(unsigned long long) * 24 * (size_t)n_ctas);
-  if (reset) { static unsigned long long z[160 * 24]; rc |= (int)cudaMemcpyToSymbol(g_eval_prof_layer, z, sizeof z); }
-  return rc;
-}
-extern "C" int spb_debug_eval_profile_v3(unsigned long long* out, int n_ctas) {
-  return (int)cudaMemcpyFromSymbol(out, g_eval_prof, sizeof(unsigned long long) * 8 * (size_t)n_ctas);
 }
 #endif
 

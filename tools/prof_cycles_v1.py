@@ -1,4 +1,5 @@
-"""Cycle attribution of the default tcgen05 evaluator (build with `make -C self-play-ai_b200/csrc PROFILE=1`)."""
+"""Cycle attribution of the FIRST tcgen05 evaluator (evaluator_umma_v1.cu, SPB_FLAG_EVAL_V1; build with
+`make -B -C self-play-ai_b200/csrc PROFILE=1`).  The default kernel is profiled with tools/trace_v2.py (VARIANT=-DSPB_TRACE)."""
 import sys, os, ctypes as C
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -8,10 +9,10 @@ if os.environ.get("SPB_LIB"):
 import selfplay_b200 as S
 from selfplay_b200.synth import synthetic_roots_device
 from selfplay_b200.weights_init import random_checkpoint
-VER = os.environ.get("SPB_VER", "v2")
+VER = "v1"
 G = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 sims = int(sys.argv[2]) if len(sys.argv) > 2 else 40
-with S.Engine(game=S.GAME_C4, num_games=G, evaluator=S.EVAL_NET, flags=S.FLAG_NO_GRAPH | (S.FLAG_EVAL_V1 if os.environ.get("SPB_VER", "v2") == "v1" else 0)) as e:
+with S.Engine(game=S.GAME_C4, num_games=G, evaluator=S.EVAL_NET, flags=S.FLAG_NO_GRAPH | S.FLAG_EVAL_V1) as e:
     e.load_weights(random_checkpoint(1, 0))
     roots = synthetic_roots_device(e, G)
     e.reset_games(roots)
