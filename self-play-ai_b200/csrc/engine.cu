@@ -109,52 +109,107 @@ __global__ void __launch_bounds__(THREADS) k_search_fused(Trees T, uint32_t num_
 // Split pipeline.  do_finish: expand + backup the leaf whose evaluation is in eval_out.
 // do_select: run the select of the next simulation; terminal leaves are backed up at once,
 // the others are appended to the evaluator's work list.
+#ifdef SPB_TRACE
+__device__ unsigned long long g_pdl_trace[64][8];   // trace build: globaltimer stamps of consecutive kernels, [i][0..2] tree step entry / after wait / exit
+__device__ unsigned int g_pdl_idx = 0;
+__device__ unsigned long long g_warp_trace[8192][6];   // per tree of the latest tree step: entry, after wait, after finish, after descend, after append, exit
+extern "C" int spb_debug_warp_trace(unsigned long long* out, int n) { return (int)cudaMemcpyFromSymbol(out, g_warp_trace, sizeof(unsigned long long) * 6 * (size_t)n); }
+#define WTRACE(i) do { if (lane == 0 && g < 8192 && do_select && do_finish) g_warp_trace[g][i] = gtimer(); } while (0)
+extern "C" int spb_debug_pdl_trace(unsigned long long* out) {
+  unsigned int z = 0;
+  int rc = (int)cudaMemcpyFromSymbol(out, g_pdl_trace, sizeof(unsigned long long) * 64 * 8);
+  rc |= (int)cudaMemcpyToSymbol(g_pdl_idx, &z, sizeof z);
+  return rc;
+}
+__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#else
+#define WTRACE(i) ((void)0)
+#endif
+
 template <class G>
 __global__ void __launch_bounds__(THREADS) k_tree_step(Trees T, int do_finish, int do_select, uint32_t parity) {
+  // Programmatic dependent launch (no-ops for a plain launch): the evaluator that follows may start its set-up while
+  // this grid runs, and this grid may have been started before the evaluator in front of it finished.
+#ifdef SPB_TRACE
+  const unsigned long long tr0 = gtimer();
+#endif
+  asm volatile("griddepcontrol.launch_dependents;");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#ifdef SPB_TRACE
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    const unsigned int i = g_pdl_idx++ & 63u;
+    g_pdl_trace[i][0] = tr0;
+    g_pdl_trace[i][1] = gtimer();
+  }
+#endif
   const int lane = threadIdx.x & 31;
   const uint32_t g = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
   if (blockIdx.x == 0 && threadIdx.x == 0) T.eval_count[(parity + 1) & 1] = 0;   // for the NEXT step's select
-  if (g >= T.G || !T.live[g]) return;
-  const uint32_t b = T.buf[g];
-  NodeRec* rec = T.rec[b] + (size_t)g * T.cap;
-  uint32_t* par = T.par[b] + (size_t)g * T.cap;
+  if (g >= T.G) return;
+  // Everything that is addressed by the tree index alone is requested in ONE round trip (the step is bound by the
+  // latency of dependent global loads, not by bandwidth): liveness, live arena, the pending leaf, its state, the
+  // evaluator's answer, the arena length and the stored path (lane d holds path node d and d + 32).
   const uint32_t slot = g;   // K == 1
   uint32_t* pathm = T.path + (size_t)slot * G::MAX_DEPTH;
+  const uint8_t live = T.live[g];
+  const uint32_t b = T.buf[g];
+  const uint32_t li = T.leaf_info[slot];
+  const PState st = T.leaf_state[slot];
+  const float* eo = T.eval_out + (size_t)slot * G::EVAL_STRIDE;
+  float probs[G::A];
+#pragma unroll
+  for (int a = 0; a < G::A; ++a) probs[a] = eo[a];
+  const float v = eo[G::A];
+  uint32_t n_nodes = T.n_nodes[g];
+  const uint32_t pn0 = pathm[lane];
+  const uint32_t pn1 = (lane + 32 < G::MAX_DEPTH) ? pathm[lane + 32] : 0u;
+  if (!live) return;
+#ifdef SPB_TRACE
+  if (lane == 0 && g < 8192 && do_select && do_finish) g_warp_trace[g][0] = tr0;
+#endif
+  WTRACE(1);
+  NodeRec* rec = T.rec[b] + (size_t)g * T.cap;
+  uint32_t* par = T.par[b] + (size_t)g * T.cap;
   unsigned long long ctr[CTR_COUNT] = {0, 0, 0, 0, 0};
   bool ok = true;
 
-  if (do_finish) {
-    const uint32_t li = T.leaf_info[slot];
-    if (li & LEAF_PENDING) {
-      const int depth = (int)(li & 0xFFu);
-      const PState st = T.leaf_state[slot];
-      const float* eo = T.eval_out + (size_t)slot * G::EVAL_STRIDE;
-      float probs[G::A];
-#pragma unroll
-      for (int a = 0; a < G::A; ++a) probs[a] = eo[a];
-      const float v = eo[G::A];
-      const uint32_t leaf = pathm[depth];
-      uint32_t n_nodes = T.n_nodes[g];
-      const uint32_t before = n_nodes;
-      if (!expand<G>(rec, par, T.cap, n_nodes, leaf, st, probs, lane)) {
-        if (lane == 0) atomicOr(T.error, ERRBIT_POOL);
-        ok = false;
-      } else {
-        ctr[CTR_CHILDREN] += n_nodes - before;
-        if (lane == 0) T.n_nodes[g] = n_nodes;
-        backup_mem(rec, pathm, depth, v, lane);
+  if (do_finish && (li & LEAF_PENDING)) {
+    const int depth = (int)(li & 0xFFu);
+    const uint32_t leaf = __shfl_sync(0xffffffffu, depth < 32 ? pn0 : pn1, depth & 31);
+    // second round trip: the path nodes' statistics (backup, mcts.rs:145-159), requested before the expand's stores
+    uint2 nw0 = make_uint2(0, 0), nw1 = make_uint2(0, 0);
+    if (lane <= depth) nw0 = *reinterpret_cast<const uint2*>(&rec[pn0]);
+    if (lane + 32 <= depth) nw1 = *reinterpret_cast<const uint2*>(&rec[pn1]);
+    const uint32_t before = n_nodes;
+    if (!expand<G>(rec, par, T.cap, n_nodes, leaf, st, probs, lane)) {
+      if (lane == 0) atomicOr(T.error, ERRBIT_POOL);
+      ok = false;
+    } else {
+      ctr[CTR_CHILDREN] += n_nodes - before;
+      if (lane == 0) T.n_nodes[g] = n_nodes;
+      if (lane <= depth) {                                        // same arithmetic as backup_mem: N += 1, W = W + (+-v)
+        nw0.x += 1u;
+        nw0.y = __float_as_uint(__fadd_rn(__uint_as_float(nw0.y), ((depth - lane) & 1) ? -v : v));
+        *reinterpret_cast<uint2*>(&rec[pn0]) = nw0;
       }
-      if (lane == 0) T.leaf_info[slot] = 0;
-      __syncwarp();
+      if (lane + 32 <= depth) {
+        nw1.x += 1u;
+        nw1.y = __float_as_uint(__fadd_rn(__uint_as_float(nw1.y), ((depth - lane - 32) & 1) ? -v : v));
+        *reinterpret_cast<uint2*>(&rec[pn1]) = nw1;
+      }
     }
+    if (lane == 0) T.leaf_info[slot] = 0;
+    __syncwarp();
   }
 
+  WTRACE(2);
   if (do_select && ok) {
     WarpPath path;
     uint32_t leaf, linfo;
     int depth;
     PState st;
     descend<G>(rec, T.root_state[g], T.c, lane, path, leaf, depth, st, linfo, T.error);
+    WTRACE(3);
     ctr[CTR_SIMS] += 1;
     ctr[CTR_PATHSUM] += (unsigned)depth;
     const uint32_t status = info_status(linfo);
@@ -176,7 +231,9 @@ __global__ void __launch_bounds__(THREADS) k_tree_step(Trees T, int do_finish, i
       }
     }
   }
+  WTRACE(4);
   flush_counters(T, ctr, lane);
+  WTRACE(5);
 }
 
 // ---- EXTENSION (not in the reference): K in-flight leaves per tree per step with virtual loss ------------
@@ -813,6 +870,23 @@ int32_t spb_engine::launch_eval_step(uint32_t parity) {
   return SPB_OK;
 }
 
+// Launch with programmatic stream serialization: the grid may begin before its predecessor in the stream has drained
+// (it blocks in griddepcontrol.wait before touching anything the predecessor writes).  Only for kernels that contain
+// that wait.
+template <class... P, class... A>
+static cudaError_t launch_pdl(void (*kernel)(P...), uint32_t blocks, uint32_t threads, cudaStream_t stream, A... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(blocks);
+  cfg.blockDim = dim3(threads);
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<P>(args)...);
+}
+
 template <class G>
 int32_t spb_engine::search_t(uint32_t num_searches) {
   if (num_searches == 0) return SPB_OK;
@@ -853,8 +927,7 @@ int32_t spb_engine::search_t(uint32_t num_searches) {
   } else {
     // step j: select writes eval_count[j&1]; the kernel also zeroes eval_count[(j+1)&1].
     SPB_CUDA(cudaMemsetAsync(T.eval_count, 0, 8, stream));
-    k_tree_step<G><<<blocks, THREADS, 0, stream>>>(T, 0, 1, 0u);
-    SPB_CHECK_LAUNCH();
+    SPB_CUDA(launch_pdl(k_tree_step<G>, blocks, THREADS, stream, T, 0, 1, 0u));
     ++launches;
     uint32_t j = 0;
     const bool use_graph = !(cfg.flags & SPB_FLAG_NO_GRAPH) && num_searches > 2;
@@ -864,12 +937,13 @@ int32_t spb_engine::search_t(uint32_t num_searches) {
         cudaGraph_t graph;
         SPB_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
         int32_t rc = launch_eval_step<G>(0u);
-        k_tree_step<G><<<blocks, THREADS, 0, stream>>>(T, 1, 1, 1u);
+        cudaError_t pe = launch_pdl(k_tree_step<G>, blocks, THREADS, stream, T, 1, 1, 1u);
         if (rc == SPB_OK) rc = launch_eval_step<G>(1u);
-        k_tree_step<G><<<blocks, THREADS, 0, stream>>>(T, 1, 1, 0u);
+        if (pe == cudaSuccess) pe = launch_pdl(k_tree_step<G>, blocks, THREADS, stream, T, 1, 1, 0u);
         cudaError_t ce = cudaStreamEndCapture(stream, &graph);
         launches -= 2;
         if (rc != SPB_OK) return rc;
+        if (ce == cudaSuccess) ce = pe;
         if (ce != cudaSuccess) { set_error(std::string("graph capture: ") + cudaGetErrorString(ce)); return SPB_ERR_CUDA; }
         SPB_CUDA(cudaGraphInstantiate(&step_graph, graph, 0));
         cudaGraphDestroy(graph);
@@ -891,8 +965,7 @@ int32_t spb_engine::search_t(uint32_t num_searches) {
         SPB_CUDA(cudaMemcpyAsync(&T.eval_count[2], &T.eval_count[j & 1u], 4, cudaMemcpyDeviceToDevice, stream));
         last_eval_parity = 2;
       }
-      k_tree_step<G><<<blocks, THREADS, 0, stream>>>(T, 1, last ? 0 : 1, j + 1);
-      SPB_CHECK_LAUNCH();
+      SPB_CUDA(launch_pdl(k_tree_step<G>, blocks, THREADS, stream, T, 1, last ? 0 : 1, j + 1));
       ++launches;
     }
   }

@@ -319,6 +319,9 @@ constexpr int STAGER_WARP = 10;
 // timeline is that of the production kernel
 __device__ unsigned long long g_trace[4][512];   // [0] MMA issue begin, [1] MMA issue end, [2] epilogue body begin, [3] body end; index (b*10+l)*4+t
 #define TRACE(k, b, l, t) do { if (blockIdx.x == 0 && (b) < 12) g_trace[k][(((b) * 10 + (l)) * 4 + (t))] = clock64(); } while (0)
+__device__ unsigned long long g_eval_times[64][4];   // globaltimer: [launch][entry, after griddepcontrol.wait, exit] of CTA 0
+__device__ unsigned int g_eval_idx = 0;
+__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 #define TRACE2(i) do { if (blockIdx.x == 0 && bb == 0 && lane == 0) g_trace[3][480 + (warp == 2 ? 0 : 8) + (i)] = clock64(); } while (0)
 #else
 #define TRACE2(i) ((void)0)
@@ -333,12 +336,13 @@ k_eval_umma(const uint8_t* __restrict__ image, const PState* __restrict__ states
   using Ge = Geo<G>;
   using Sm = Smem<G>;
   extern __shared__ __align__(1024) uint8_t smem[];
-  const uint32_t n_total = min(*count_dev, max_n);
-  const uint32_t cta = blockIdx.x, ncta = gridDim.x;
-  const uint32_t my_begin = (uint32_t)(((uint64_t)n_total * cta) / ncta);
-  const uint32_t my_end = (uint32_t)(((uint64_t)n_total * (cta + 1)) / ncta);
-  if (my_begin >= my_end) return;                                  // uniform per CTA
-
+  // Programmatic dependent launch: this grid may start while the tree-step kernel that produces its work list is
+  // still running.  Everything up to griddepcontrol.wait touches only shared memory, TMEM and the (static) weight
+  // image; the work list, its length and the leaf states are read after the wait.
+#ifdef SPB_TRACE
+  const unsigned long long tr_entry = gtimer();
+#endif
+  asm volatile("griddepcontrol.launch_dependents;");
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t s_base = smem_u32(smem);
   const uint32_t bar_base = s_base + Sm::OFF_BARS;
@@ -378,7 +382,15 @@ k_eval_umma(const uint8_t* __restrict__ image, const PState* __restrict__ states
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const uint32_t n_batches = (my_end - my_begin + Ge::NB - 1) / Ge::NB;
+  asm volatile("griddepcontrol.wait;" ::: "memory");              // the producer grid has completed and its writes are visible
+#ifdef SPB_TRACE
+  const unsigned long long tr_wait = gtimer();
+#endif
+  const uint32_t n_total = min(__ldcg(count_dev), max_n);
+  const uint32_t cta = blockIdx.x, ncta = gridDim.x;
+  const uint32_t my_begin = (uint32_t)(((uint64_t)n_total * cta) / ncta);
+  const uint32_t my_end = (uint32_t)(((uint64_t)n_total * (cta + 1)) / ncta);
+  const uint32_t n_batches = (my_end - my_begin + Ge::NB - 1) / Ge::NB;   // 0: this CTA only frees its TMEM
 
   if (warp == 0) {
     // ===== weight producer: streams (layer, tap) blocks into the 9-slot ring ==========================
@@ -466,9 +478,10 @@ k_eval_umma(const uint8_t* __restrict__ image, const PState* __restrict__ states
       const int nt = (int)((nb * Ge::BS + 127) / 128);
       PState st_mine = PState{};
       uint32_t slot_mine = 0;
-      if ((uint32_t)lane < nb) {
-        slot_mine = list ? list[b0 + lane] : (b0 + lane);
-        st_mine = states[slot_mine];
+      if ((uint32_t)lane < nb) {                                  // written by the grid before this one: bypass L1
+        slot_mine = list ? __ldcg(list + b0 + lane) : (b0 + lane);
+        const ulonglong2 raw = __ldcg(reinterpret_cast<const ulonglong2*>(states + slot_mine));
+        st_mine.x = raw.x; st_mine.o = raw.y;
       }
       if (bb > 0) mbar_wait_backoff<64>(bar_act0_free, (bb - 1) & 1u);
       PState* st_buf = s_states + (bb & 1u) * Ge::NB;
@@ -745,7 +758,7 @@ k_eval_umma(const uint8_t* __restrict__ image, const PState* __restrict__ states
       TRACE2(5);
     };
 
-    conv_epilogue(0, 0);
+    if (n_batches > 0) conv_epilogue(0, 0);
     for (uint32_t b = 0; b < n_batches; ++b) {
       for (int l = 1; l < 9; ++l) conv_epilogue(b, l);
       head_epilogue(b);
@@ -761,6 +774,12 @@ k_eval_umma(const uint8_t* __restrict__ image, const PState* __restrict__ states
   tc_fence_before();
   __syncthreads();
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+#ifdef SPB_TRACE
+  if (blockIdx.x == 0 && tid == 0) {
+    const unsigned int i = g_eval_idx++ & 63u;
+    g_eval_times[i][0] = tr_entry; g_eval_times[i][1] = tr_wait; g_eval_times[i][2] = gtimer();
+  }
+#endif
 }
 
 template <class G>
@@ -785,12 +804,28 @@ static cudaError_t launch_t(const Evaluator::DevNet& net, const PState* states, 
     sm_count = sm_counts[dev];
   }
   const unsigned grid = (unsigned)std::max(1, std::min<int>(sm_count, (int)max_n));
-  k_eval_umma<G><<<grid, THREADS, Smem<G>::TOTAL, stream>>>(reinterpret_cast<const uint8_t*>(net.w_umma), states, list, count_dev, max_n,
-                                                            out, stride, logits_out);
-  return cudaGetLastError();
+  // programmatic stream serialization: the kernel may start (set-up only) before the previous kernel in the stream ends
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = Smem<G>::TOTAL;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, k_eval_umma<G>, reinterpret_cast<const uint8_t*>(net.w_umma), states, list, count_dev, max_n, out, stride,
+                            logits_out);
 }
 
 #ifdef SPB_TRACE
+extern "C" int spb_debug_eval_times_v2(unsigned long long* out) {
+  unsigned int z = 0;
+  int rc = (int)cudaMemcpyFromSymbol(out, g_eval_times, sizeof(unsigned long long) * 64 * 4);
+  rc |= (int)cudaMemcpyToSymbol(g_eval_idx, &z, sizeof z);
+  return rc;
+}
 extern "C" int spb_debug_trace_v2(unsigned long long* out, int reset) {
   int rc = (int)cudaMemcpyFromSymbol(out, g_trace, sizeof(unsigned long long) * 4 * 512);
   if (reset) { static unsigned long long z[4 * 512]; rc |= (int)cudaMemcpyToSymbol(g_trace, z, sizeof z); }
