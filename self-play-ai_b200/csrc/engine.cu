@@ -573,7 +573,7 @@ __global__ void __launch_bounds__(THREADS) k_selfplay_step(Trees T, SelfPlay P, 
     chosen = ball ? __ffs((int)ball) - 1 : (int)nc - 1;
   } else {
     // main.rs:108-112: max_by(total_cmp) over visit counts -> the LAST maximal child.
-    chosen = warp_argmax_last(lane < (int)nc ? (float)cnt : -INFINITY, lane < (int)nc ? lane : -1);
+    chosen = warp_argmax_last<G::A>(lane < (int)nc ? (float)cnt : -INFINITY, lane < (int)nc ? lane : -1);
     chosen = __shfl_sync(0xffffffffu, chosen, 0);
   }
   // learner_concurrent.rs:197-198: push root state + visit-count policy.

@@ -71,7 +71,7 @@ struct Trees {
 __device__ __forceinline__ float puct_score(float c, uint32_t n_parent, uint32_t n_child, float w_child, float prior) {
   float q = 0.0f;                                              // :95 unvisited child -> q = 0.0
   if (n_child != 0)
-    q = __fdiv_rn(__fadd_rn(__fdiv_rn(-w_child, (float)n_child), 1.0f), 2.0f);   // :97
+    q = __fmul_rn(__fadd_rn(__fdiv_rn(-w_child, (float)n_child), 1.0f), 0.5f);   // :97 (x / 2.0 and x * 0.5 round identically)
   float u = __fmul_rn(c, prior);
   u = __fmul_rn(u, __fsqrt_rn((float)n_parent));
   u = __fdiv_rn(u, __fadd_rn(1.0f, (float)n_child));
@@ -80,14 +80,15 @@ __device__ __forceinline__ float puct_score(float c, uint32_t n_parent, uint32_t
 
 // select, mcts.rs:102-114: arg-max over the children with Iterator::max_by semantics — among equal
 // maxima the LAST child wins.  Lanes >= nc carry (-inf, -1).  Returns the winning child index.
+template <int MAX_CHILDREN>
 __device__ __forceinline__ int warp_argmax_last(float score, int idx) {
 #pragma unroll
-  for (int off = 8; off >= 1; off >>= 1) {
+  for (int off = (MAX_CHILDREN > 8 ? 8 : 4); off >= 1; off >>= 1) {   // butterfly over the 8 / 16 lanes that can hold a child
     float os = __shfl_xor_sync(0xffffffffu, score, off);
     int oi = __shfl_xor_sync(0xffffffffu, idx, off);
     if (os > score || (os == score && oi > idx)) { score = os; idx = oi; }
   }
-  return idx;   // lanes 0..15 agree; callers broadcast from lane 0
+  return idx;   // the lanes of the butterfly agree; callers broadcast from lane 0
 }
 
 // Path of one simulation, distributed over the warp: lane d holds depth d (set 0) and depth d+32 (set 1).
@@ -121,7 +122,7 @@ __device__ __forceinline__ void descend(const NodeRec* rec, const PState& root, 
       idx = lane;
       if (score != score) atomicOr(err, ERRBIT_NAN);         // the reference would panic (partial_cmp().unwrap())
     }
-    int best = warp_argmax_last(score, idx);
+    int best = warp_argmax_last<G::A>(score, idx);
     best = __shfl_sync(0xffffffffu, best, 0);
     uint32_t bN = __shfl_sync(0xffffffffu, ch.N, best);
     float bW = __shfl_sync(0xffffffffu, ch.W, best);
