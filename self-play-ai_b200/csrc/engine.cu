@@ -1543,10 +1543,10 @@ int32_t spb_time_evaluator(spb_engine* e, uint32_t iters, float* avg_ms, uint32_
   const bool simt = (e->cfg.flags & SPB_FLAG_EVAL_SIMT) != 0;
   cudaError_t ce = cudaSuccess;
   for (int w = 0; w < 2 && ce == cudaSuccess; ++w)    // warm-up
-    ce = e->evaluator.launch(e->T.leaf_state, e->T.eval_list, cnt, slots, e->T.eval_out, e->eval_stride, nullptr, simt, e->stream);
+    ce = e->evaluator.launch(e->T.leaf_state, e->T.eval_list, cnt, slots, e->T.eval_out, e->eval_stride, nullptr, simt, e->stream, /*overlap=*/false);
   if (ce == cudaSuccess) ce = cudaEventRecord(e->ev0, e->stream);
   for (uint32_t i = 0; i < iters && ce == cudaSuccess; ++i)
-    ce = e->evaluator.launch(e->T.leaf_state, e->T.eval_list, cnt, slots, e->T.eval_out, e->eval_stride, nullptr, simt, e->stream);
+    ce = e->evaluator.launch(e->T.leaf_state, e->T.eval_list, cnt, slots, e->T.eval_out, e->eval_stride, nullptr, simt, e->stream, /*overlap=*/false);
   if (ce == cudaSuccess) ce = cudaEventRecord(e->ev1, e->stream);
   uint32_t n = 0;
   if (ce == cudaSuccess) ce = cudaMemcpyAsync(&n, cnt, 4, cudaMemcpyDeviceToHost, e->stream);

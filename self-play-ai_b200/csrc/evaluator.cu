@@ -197,7 +197,7 @@ bool Evaluator::upload(const HostNet& net, std::string* err) {
 }
 
 cudaError_t Evaluator::launch(const PState* states, const uint32_t* list, const uint32_t* count_dev, uint32_t max_n, float* out,
-                              int stride, float* logits_out, bool simt, cudaStream_t stream) {
+                              int stride, float* logits_out, bool simt, cudaStream_t stream, bool overlap) {
   if (!loaded_) return cudaErrorNotReady;
   if (simt) {
     const unsigned grid = std::min<unsigned>(max_n, 148u * 4u);
@@ -217,7 +217,7 @@ cudaError_t Evaluator::launch(const PState* states, const uint32_t* list, const 
     return umma_v3::launch(net, game_, states, list, count_dev, max_n, out, stride, logits_out, stream);
   }
   net.w_umma = dev_.w_umma_v2;
-  return umma_v2::launch(net, game_, states, list, count_dev, max_n, out, stride, logits_out, stream);
+  return umma_v2::launch(net, game_, states, list, count_dev, max_n, out, stride, logits_out, stream, overlap);
 }
 
 }  // namespace spb

@@ -52,7 +52,7 @@ class Evaluator {
   // logits_out (nullable) receives raw logits at [list[i]*A + a].  list == nullptr means identity.
   // simt = true selects the CUDA-core cross-check kernel instead of the tcgen05 kernel.
   cudaError_t launch(const PState* states, const uint32_t* list, const uint32_t* count_dev, uint32_t max_n,
-                     float* out, int stride, float* logits_out, bool simt, cudaStream_t stream);
+                     float* out, int stride, float* logits_out, bool simt, cudaStream_t stream, bool overlap = true);
 
   // FLOPs per evaluated position (2*MAC over convs and FCs; SURVEY.md §8a: 26,630,268 for Connect4).
   double flops_per_position() const;

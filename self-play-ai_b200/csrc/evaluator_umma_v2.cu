@@ -784,7 +784,7 @@ k_eval_umma(const uint8_t* __restrict__ image, const PState* __restrict__ states
 
 template <class G>
 static cudaError_t launch_t(const Evaluator::DevNet& net, const PState* states, const uint32_t* list, const uint32_t* count_dev,
-                            uint32_t max_n, float* out, int stride, float* logits_out, cudaStream_t stream) {
+                            uint32_t max_n, float* out, int stride, float* logits_out, cudaStream_t stream, bool overlap) {
   // per device (one process may drive one engine per GPU from several host threads): SM count + opt-in shared memory
   static std::mutex mu;
   static int sm_counts[64] = {};
@@ -812,7 +812,7 @@ static cudaError_t launch_t(const Evaluator::DevNet& net, const PState* states, 
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  attr[0].val.programmaticStreamSerializationAllowed = overlap ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, k_eval_umma<G>, reinterpret_cast<const uint8_t*>(net.w_umma), states, list, count_dev, max_n, out, stride,
@@ -834,9 +834,9 @@ extern "C" int spb_debug_trace_v2(unsigned long long* out, int reset) {
 #endif
 
 cudaError_t launch(const Evaluator::DevNet& net, int game, const PState* states, const uint32_t* list, const uint32_t* count_dev,
-                   uint32_t max_n, float* out, int stride, float* logits_out, cudaStream_t stream) {
-  if (game == SPB_GAME_CONNECT4) return launch_t<Connect4>(net, states, list, count_dev, max_n, out, stride, logits_out, stream);
-  return launch_t<TicTacToe>(net, states, list, count_dev, max_n, out, stride, logits_out, stream);
+                   uint32_t max_n, float* out, int stride, float* logits_out, cudaStream_t stream, bool overlap) {
+  if (game == SPB_GAME_CONNECT4) return launch_t<Connect4>(net, states, list, count_dev, max_n, out, stride, logits_out, stream, overlap);
+  return launch_t<TicTacToe>(net, states, list, count_dev, max_n, out, stride, logits_out, stream, overlap);
 }
 
 }  // namespace umma_v2
