@@ -70,6 +70,12 @@ struct Connect4 {
     return m;
   }
 
+  // One action's legality (same rule as valid_mask, for a position that is still being played): lane a of a warp
+  // tests column a, a ballot then gives the legal mask without a 7-step loop.
+  __device__ __forceinline__ static bool action_legal(const PState& s, int a) {
+    return (((ps_x(s) | ps_o(s)) >> (a * 7 + 5)) & 1ull) == 0;
+  }
+
   // get_winner, connect_four.rs:139-180, literally: any four in the latest ROW (either player),
   // any four in the latest COLUMN, and the (row+i, col+i) diagonal windows i in [start,end]
   // (:164-166).  The anti-diagonal is NOT checked — reference behaviour, reproduced on purpose.
@@ -154,6 +160,9 @@ struct TicTacToe {
     if (ps_status(s) != SPB_STATUS_ONGOING) return 0u;
     return (uint32_t)(~(ps_x(s) | ps_o(s))) & 0x1FFu;
   }
+  __device__ __forceinline__ static bool action_legal(const PState& s, int a) {
+    return (((uint32_t)(ps_x(s) | ps_o(s)) >> a) & 1u) == 0;
+  }
 
   // get_next_state, tictactoe.rs:135-167.
   __device__ __forceinline__ static bool next_state(const PState& s, int action, PState* out) {
@@ -215,6 +224,19 @@ __device__ __forceinline__ void mask_renorm(uint32_t legal, const float* probs, 
   float s = G::masked_sum(m);
 #pragma unroll
   for (int a = 0; a < G::A; ++a) out[a] = __fdiv_rn(m[a], s);
+}
+
+// The same, for ONE action: expand needs only the prior of the child a lane creates (one IEEE division instead of A).
+template <class G>
+__device__ __forceinline__ float mask_renorm_one(uint32_t legal, const float* probs, int action) {
+  float m[G::A];
+#pragma unroll
+  for (int a = 0; a < G::A; ++a) m[a] = __fmul_rn(probs[a], (legal >> a & 1u) ? 1.0f : 0.0f);
+  const float s = G::masked_sum(m);
+  float mine = 0.0f;
+#pragma unroll
+  for (int a = 0; a < G::A; ++a) if (a == action) mine = m[a];
+  return __fdiv_rn(mine, s);
 }
 
 // ---- DetEval ---------------------------------------------------------------

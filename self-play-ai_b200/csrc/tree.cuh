@@ -127,14 +127,19 @@ __device__ __forceinline__ void descend(const NodeRec* rec, const PState& root, 
     uint32_t bN = __shfl_sync(0xffffffffu, ch.N, best);
     float bW = __shfl_sync(0xffffffffu, ch.W, best);
     uint32_t binfo = __shfl_sync(0xffffffffu, ch.info, best);
-    uint32_t legal = G::valid_mask(st);
-    int action = nth_set_bit(legal, best);
+    // The children are in ascending action order (expand): child `best` is the action whose rank among the legal
+    // actions is `best`.  Lane a tests action a; two ballots replace the mask loop and the n-th-set-bit search.
+    const bool lb = lane < G::A && G::action_legal(st, lane);
+    const uint32_t legal = __ballot_sync(0xffffffffu, lb);
+    const uint32_t hit = __ballot_sync(0xffffffffu, lb && __popc(legal & ((1u << lane) - 1u)) == best);
+    const int action = __ffs((int)hit) - 1;
     st = G::place(st, action, info_status(binfo));
     node = fc + (uint32_t)best;
     ++depth;
-    if (lane == (depth & 31)) {
-      int s = depth >> 5;
-      path.node[s] = node; path.N[s] = bN; path.W[s] = bW;
+    if (depth < 32) {                                        // static register indices: no select chains
+      if (lane == depth) { path.node[0] = node; path.N[0] = bN; path.W[0] = bW; }
+    } else if (lane == depth - 32) {
+      path.node[1] = node; path.N[1] = bN; path.W[1] = bW;
     }
     Np = bN;
     info = binfo;
@@ -177,24 +182,24 @@ __device__ __forceinline__ void backup_mem(NodeRec* rec, const uint32_t* path, i
 template <class G>
 __device__ __forceinline__ bool expand(NodeRec* rec, uint32_t* par, uint32_t cap, uint32_t& n_nodes, uint32_t leaf,
                                        const PState& st, const float* probs, int lane) {
-  const uint32_t legal = G::valid_mask(st);
+  // Lane a tests action a (the leaf is an ongoing position); the ballot is get_valid_actions' mask and the rank of a
+  // legal action among the legal ones is its child index, so children come out in ascending action order.
+  const bool lb = lane < G::A && G::action_legal(st, lane);
+  const uint32_t legal = __ballot_sync(0xffffffffu, lb);
   const int nc = __popc(legal);
   const uint32_t first = n_nodes;
   if (first + (uint32_t)nc > cap) return false;
-  float priors[G::A];
-  mask_renorm<G>(legal, probs, priors);
-  if (lane < nc) {
-    int a = nth_set_bit(legal, lane);
+  if (lb) {
+    const int a = lane;
+    const uint32_t ci = first + (uint32_t)__popc(legal & ((1u << lane) - 1u));
     PState child;
     G::next_state(st, a, &child);                            // :129 (cannot fail: a is legal)
-    float p = 0.0f;
-#pragma unroll
-    for (int k = 0; k < G::A; ++k) if (k == a) p = priors[k];   // :128 policy.get_prob(&action)
+    const float p = mask_renorm_one<G>(legal, probs, a);     // :128 policy.get_prob(&action) of the masked, renormalised policy
     NodeRec r;
     r.N = 0; r.W = 0.0f; r.P = p;
     r.info = make_info(0, 0, ps_status(child));
-    rec[first + lane] = r;
-    par[first + lane] = leaf | ((uint32_t)a << 24);
+    rec[ci] = r;
+    par[ci] = leaf | ((uint32_t)a << 24);
   }
   if (lane == 0) rec[leaf].info = make_info(first, (uint32_t)nc, SPB_STATUS_ONGOING);
   n_nodes = first + (uint32_t)nc;
