@@ -152,3 +152,51 @@ def test_full_size_selfplay_trajectories_replay_through_the_oracle_rules():
         for i in idx:
             want = value if int(pos[i]["current_player"]) == final_mover else -value
             assert int(pos[i]["outcome"]) == want
+
+
+def test_full_size_tictactoe_sampled_oracle_and_pipeline_agreement():
+    """configs[0] at scale: 4,096 tic-tac-toe games x 200 simulations — the trees exhaust the game below most roots, so
+    terminal-leaf backups dominate; sampled trees bit-exact vs the oracle, fused == lock-step for all of them."""
+    sims = 200
+    sample = list(range(3, G, 293))
+    f = O.Forest(O.GAME_TTT, len(sample))
+    digests = []
+    for flags in (0, S.FLAG_FORCE_SPLIT):
+        with S.Engine(game=S.GAME_TTT, num_games=G, evaluator=S.EVAL_DET, flags=flags) as e:
+            roots = synthetic_roots_device(e, G, max_ply=5)
+            e.reset_games(roots)
+            e.reset_counters()
+            e.search(sims)
+            d, counts, n = _digest(e)
+            assert (counts.sum(axis=1) == sims - 1).all()
+            ctr = e.counters()
+            assert ctr["simulations"] == G * sims and ctr["evaluations"] + ctr["terminal_leaves"] == G * sims
+            digests.append((d, ctr["path_length_sum"], ctr["children_created"], ctr["terminal_leaves"]))
+            if flags == 0:
+                f.reset([O.state_from_record(roots[g]) for g in sample])
+                f.search(sims, O.EVAL_DET)
+            for k, g in enumerate(sample):
+                assert e.root_children(g) == f.root_children(k), g
+                assert e.arena_len(g) == f.arena_len(k)
+                assert e.node_stats(g, 0) == f.node_stats(k, 0)
+    assert digests[0] == digests[1]
+
+
+def test_full_size_network_with_16_leaves_in_flight_conserves_the_budget():
+    """configs[3] with the real evaluator: 4,096 trees x 16 leaves per step = up to 65,536 positions per evaluator launch."""
+    K = 16
+    with S.Engine(game=S.GAME_C4, num_games=G, evaluator=S.EVAL_NET, leaves_per_tree=K) as e:
+        e.load_weights(random_checkpoint(1, 0))
+        roots = synthetic_roots_device(e, G)
+        seen = []
+        for _ in range(2):
+            e.reset_games(roots)
+            e.reset_counters()
+            e.search(SIMS)
+            d, counts, n = _digest(e)
+            assert (counts.sum(axis=1) == SIMS - K).all()
+            ctr = e.counters()
+            assert ctr["simulations"] == G * SIMS
+            assert e.node_stats(17, 0)["visit_count"] == SIMS
+            seen.append(d)
+        assert seen[0] == seen[1]
