@@ -214,7 +214,7 @@ cudaError_t Evaluator::launch(const PState* states, const uint32_t* list, const 
   }
   if (use_v3_) {
     net.w_umma = dev_.w_umma_v3;
-    return umma_v3::launch(net, game_, states, list, count_dev, max_n, out, stride, logits_out, stream);
+    return umma_v3::launch(net, game_, states, list, count_dev, max_n, out, stride, logits_out, stream, overlap);
   }
   net.w_umma = dev_.w_umma_v2;
   return umma_v2::launch(net, game_, states, list, count_dev, max_n, out, stride, logits_out, stream, overlap);

@@ -25,6 +25,6 @@ namespace umma_v3 {   // the kx-pair kernel on CTA pairs (cta_group::2, each CTA
 void pack_weights(const HostNet& net, std::vector<uint8_t>* out);
 cudaError_t launch(const Evaluator::DevNet& net, int game, const PState* states, const uint32_t* list,
                    const uint32_t* count_dev, uint32_t max_n, float* out, int stride, float* logits_out,
-                   cudaStream_t stream);
+                   cudaStream_t stream, bool overlap);
 }  // namespace umma_v3
 }  // namespace spb

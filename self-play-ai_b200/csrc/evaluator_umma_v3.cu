@@ -392,13 +392,12 @@ k_eval_umma(const uint8_t* __restrict__ image, const PState* __restrict__ states
   using Ge = Geo<G>;
   using Sm = Smem<G>;
   extern __shared__ __align__(1024) uint8_t smem[];
-  const uint32_t n_total = min(*count_dev, max_n);
+  // Programmatic dependent launch: everything up to griddepcontrol.wait touches only shared memory, TMEM and the
+  // (static) weight image; the work list, its length and the leaf states are read after the wait.
+  asm volatile("griddepcontrol.launch_dependents;");
   const uint32_t rank = cluster_ctarank();                         // 0 = leader (issues the MMAs of the pair)
   const uint32_t cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;
-  const uint32_t cl_begin = (uint32_t)(((uint64_t)n_total * cid) / ncl);
-  const uint32_t cl_end = (uint32_t)(((uint64_t)n_total * (cid + 1)) / ncl);
-  if (cl_begin >= cl_end) return;                                  // uniform per cluster
-  const uint32_t n_batches = (cl_end - cl_begin + 2 * Ge::NB - 1) / (2 * Ge::NB);
+  uint32_t cl_begin = 0, cl_end = 0, n_batches = 0;                // set after the wait
   // Batch bb of the pair: up to 2*NB boards, the leader takes the first half (rounded up); both CTAs run the leader's
   // tile count so that their barrier phases stay aligned (the peer's extra rows are zero boards).
   auto batch_geom = [&](uint32_t bb, uint32_t* b0, uint32_t* nb, int* nt) {
@@ -447,6 +446,14 @@ k_eval_umma(const uint8_t* __restrict__ image, const PState* __restrict__ states
   cluster_sync();                                                  // both CTAs' barriers exist before anything arrives remotely
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+
+  asm volatile("griddepcontrol.wait;" ::: "memory");              // the producer grid has completed and its writes are visible
+  {
+    const uint32_t n_total = min(__ldcg(count_dev), max_n);
+    cl_begin = (uint32_t)(((uint64_t)n_total * cid) / ncl);
+    cl_end = (uint32_t)(((uint64_t)n_total * (cid + 1)) / ncl);
+    n_batches = (cl_end - cl_begin + 2 * Ge::NB - 1) / (2 * Ge::NB);   // 0: this pair only frees its TMEM
+  }
 
   if (warp == 0) {
     // ===== weight producer ===========================================================================
@@ -540,9 +547,10 @@ k_eval_umma(const uint8_t* __restrict__ image, const PState* __restrict__ states
       batch_geom(bb, &b0, &nb, &nt);
       PState st_mine = PState{};
       uint32_t slot_mine = 0;
-      if ((uint32_t)lane < nb) {
-        slot_mine = list ? list[b0 + lane] : (b0 + lane);
-        st_mine = states[slot_mine];
+      if ((uint32_t)lane < nb) {                                  // written by the grid before this one: bypass L1
+        slot_mine = list ? __ldcg(list + b0 + lane) : (b0 + lane);
+        const ulonglong2 raw = __ldcg(reinterpret_cast<const ulonglong2*>(states + slot_mine));
+        st_mine.x = raw.x; st_mine.o = raw.y;
       }
       if (bb > 0) mbar_wait_backoff<64>(bar_act0_free, (bb - 1) & 1u);
       PState* st_buf = s_states + (bb & 1u) * Ge::NB;
@@ -828,7 +836,7 @@ k_eval_umma(const uint8_t* __restrict__ image, const PState* __restrict__ states
       TRACE2(5);
     };
 
-    conv_epilogue(0, 0);
+    if (n_batches > 0) conv_epilogue(0, 0);
     for (uint32_t b = 0; b < n_batches; ++b) {
       for (int l = 1; l < 9; ++l) conv_epilogue(b, l);
       head_epilogue(b);
@@ -849,7 +857,7 @@ k_eval_umma(const uint8_t* __restrict__ image, const PState* __restrict__ states
 
 template <class G>
 static cudaError_t launch_t(const Evaluator::DevNet& net, const PState* states, const uint32_t* list, const uint32_t* count_dev,
-                            uint32_t max_n, float* out, int stride, float* logits_out, cudaStream_t stream) {
+                            uint32_t max_n, float* out, int stride, float* logits_out, cudaStream_t stream, bool overlap) {
   // per device (one process may drive one engine per GPU from several host threads): SM count + opt-in shared memory
   static std::mutex mu;
   static int sm_counts[64] = {};
@@ -869,9 +877,19 @@ static cudaError_t launch_t(const Evaluator::DevNet& net, const PState* states, 
     sm_count = sm_counts[dev];
   }
   const unsigned grid = 2u * (unsigned)std::max(1, std::min<int>(sm_count / 2, ((int)max_n + 1) / 2));   // CTA pairs
-  k_eval_umma<G><<<grid, THREADS, Smem<G>::TOTAL, stream>>>(reinterpret_cast<const uint8_t*>(net.w_umma), states, list, count_dev, max_n,
-                                                            out, stride, logits_out);
-  return cudaGetLastError();
+  // cluster dimensions come from the kernel's __cluster_dims__; programmatic stream serialization as in the default kernel
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = Smem<G>::TOTAL;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = overlap ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, k_eval_umma<G>, reinterpret_cast<const uint8_t*>(net.w_umma), states, list, count_dev, max_n, out, stride,
+                            logits_out);
 }
 
 #ifdef SPB_TRACE
@@ -883,9 +901,9 @@ extern "C" int spb_debug_trace_v3(unsigned long long* out, int reset) {
 #endif
 
 cudaError_t launch(const Evaluator::DevNet& net, int game, const PState* states, const uint32_t* list, const uint32_t* count_dev,
-                   uint32_t max_n, float* out, int stride, float* logits_out, cudaStream_t stream) {
-  if (game == SPB_GAME_CONNECT4) return launch_t<Connect4>(net, states, list, count_dev, max_n, out, stride, logits_out, stream);
-  return launch_t<TicTacToe>(net, states, list, count_dev, max_n, out, stride, logits_out, stream);
+                   uint32_t max_n, float* out, int stride, float* logits_out, cudaStream_t stream, bool overlap) {
+  if (game == SPB_GAME_CONNECT4) return launch_t<Connect4>(net, states, list, count_dev, max_n, out, stride, logits_out, stream, overlap);
+  return launch_t<TicTacToe>(net, states, list, count_dev, max_n, out, stride, logits_out, stream, overlap);
 }
 
 }  // namespace umma_v3
