@@ -69,11 +69,11 @@ def test_full_size_deterministic_evaluator_sampled_oracle_and_pipeline_agreement
 
 def test_full_size_network_search_is_conserving_and_reproducible():
     """The tcgen05 evaluator reduces in a fixed order per board, so the result of a search does not depend on how
-    leaves were batched: two searches from the same roots, and the CUDA-graph and direct-launch pipelines, give
-    identical visit counts for all 4,096 trees."""
+    leaves were batched: two searches from the same roots, the CUDA-graph and direct-launch pipelines and the CTA-pair
+    evaluator give identical visit counts for all 4,096 trees."""
     blob = random_checkpoint(1, 0)
     seen = []
-    for flags in (0, S.FLAG_NO_GRAPH):
+    for flags in (0, S.FLAG_NO_GRAPH, S.FLAG_EVAL_PAIR2):          # the CTA-pair kernel computes in the same order: same trees
         with S.Engine(game=S.GAME_C4, num_games=G, evaluator=S.EVAL_NET, flags=flags) as e:
             e.load_weights(blob)
             roots = synthetic_roots_device(e, G)
