@@ -88,3 +88,22 @@ def test_tch_names_look_like_a_varstore():
     assert "bias" in names and "weight" in names and "running_mean" in names
     assert any(re.fullmatch(r"weight__\d+", n) for n in names)
     assert len(names) == 70     # 70 VarStore tensors
+
+
+def test_flag_and_code_constants_agree_across_header_python_and_rust():
+    """The header is the source of truth; the ctypes mirror and the Rust -sys crate must not drift from it."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    header = open(os.path.join(root, "include", "selfplay_b200.h")).read()
+    defs = {m.group(1): int(m.group(2).rstrip("u"), 0) for m in re.finditer(r"#define\s+(SPB_[A-Z0-9_]+)\s+(-?\d+u?)\b", header)}
+    py = {"SPB_FLAG_NO_GRAPH": S.FLAG_NO_GRAPH, "SPB_FLAG_EVAL_SIMT": S.FLAG_EVAL_SIMT, "SPB_FLAG_FORCE_SPLIT": S.FLAG_FORCE_SPLIT,
+          "SPB_FLAG_FIXED_POOL": S.FLAG_FIXED_POOL, "SPB_FLAG_EVAL_V1": S.FLAG_EVAL_V1, "SPB_FLAG_EVAL_PAIR2": S.FLAG_EVAL_PAIR2,
+          "SPB_GAME_CONNECT4": S.GAME_C4, "SPB_GAME_TICTACTOE": S.GAME_TTT,
+          "SPB_EVAL_NET": S.EVAL_NET, "SPB_EVAL_DET": S.EVAL_DET, "SPB_EVAL_UNIFORM": S.EVAL_UNIFORM}
+    for name, value in py.items():
+        assert defs[name] == value, name
+    flags = [v for k, v in defs.items() if k.startswith("SPB_FLAG_")]
+    assert len(set(flags)) == len(flags) and all(v & (v - 1) == 0 for v in flags)      # distinct single bits
+    rust = open(os.path.join(root, "rust", "selfplay-b200-sys", "src", "lib.rs")).read()
+    for m in re.finditer(r"pub const (SPB_[A-Z0-9_]+): [iu]32 = (-?\d+);", rust):
+        assert defs[m.group(1)] == int(m.group(2)), m.group(1)
