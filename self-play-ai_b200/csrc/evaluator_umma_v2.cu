@@ -89,14 +89,31 @@ static void pack_t(const HostNet& net, std::vector<uint8_t>* out) {
       }
       continue;
     }
-    for (int tap = 0; tap < 9; ++tap) {
+    if (l == 9) {
+      // fused head conv (32 policy + 3 value + 13 zero channels), same kx-pair form: per kernel row a 12 KB pair block
+      // [8 chunks][96 n][8] (n < 48: centre tap, n >= 48: right tap) followed by the 6 KB left-tap block [8 chunks][48 n][8]
+      for (int ky = 0; ky < 3; ++ky) {
+        uint16_t* pair = reinterpret_cast<uint16_t*>(img + layer_offset(l) + (size_t)ky * 3 * layer_tap_bytes(l));
+        uint16_t* left = pair + 8 * 96 * 8;
+        for (int n = 0; n < NET_POLICY_CH + NET_VALUE_CH; ++n) {
+          const HostNet::Conv& cv = n < NET_POLICY_CH ? net.conv[9] : net.conv[10];
+          const int oc = n < NET_POLICY_CH ? n : n - NET_POLICY_CH;
+          for (int k = 0; k < 64; ++k) {
+            const float* w9 = &cv.w[((size_t)oc * cv.ic + k) * 9 + ky * 3];
+            pair[((size_t)(k / 8) * 96 + n) * 8 + (k % 8)] = f2bf(w9[1]);
+            pair[((size_t)(k / 8) * 96 + HEAD_N + n) * 8 + (k % 8)] = f2bf(w9[2]);
+            left[((size_t)(k / 8) * HEAD_N + n) * 8 + (k % 8)] = f2bf(w9[0]);
+          }
+        }
+      }
+      continue;
+    }
+    for (int tap = 0; tap < 9; ++tap) {                          // stem: one block per tap
       uint16_t* blk = reinterpret_cast<uint16_t*>(img + layer_offset(l) + (size_t)tap * layer_tap_bytes(l));
       for (int n = 0; n < N; ++n) {
         const HostNet::Conv* cv;
         int oc;
         if (l < 9) { cv = &net.conv[l]; oc = n; }
-        else if (n < NET_POLICY_CH) { cv = &net.conv[9]; oc = n; }
-        else if (n < NET_POLICY_CH + NET_VALUE_CH) { cv = &net.conv[10]; oc = n - NET_POLICY_CH; }
         else continue;
         for (int k = 0; k < KC * 8; ++k) {
           if (k >= cv->ic) break;
@@ -253,12 +270,14 @@ __device__ __forceinline__ void issue_tile(bool issuer, uint32_t a_lo_tile, uint
 // Residual conv, kx-pair form: per kernel row ky 4 MMAs of N=128 (centre | right taps, A shifted by (ky-1)*W8) and
 // 4 MMAs of N=64 (left tap, A shifted one row further back).  Ring slots 3ky, 3ky+1 hold the pair block (K chunks
 // 0..3 / 4..7), slot 3ky+2 the left tap.
-template <int W8, int Q>
+// NP = width of the pair operand (128 residual, 96 head), NL = width of the left tap (64 / 48), LEFT16 = offset of the
+// left-tap block inside the kernel row's ring group in 16-byte units.
+template <int W8, int Q, int NP, int NL, int LEFT16>
 __device__ __forceinline__ void issue_tile_pair(bool issuer, uint32_t a_lo_tile, uint32_t b_lo_base, uint32_t d_tmem,
                                                 bool first_tile, bool last_tile, uint32_t w_par, uint32_t bar_base,
                                                 uint32_t mid_bar, uint32_t mid_par) {
   constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);
-  constexpr uint32_t IDESC128 = make_idesc(128), IDESC64 = make_idesc(64);
+  constexpr uint32_t IDESC128 = make_idesc(NP), IDESC64 = make_idesc(NL);
 #pragma unroll
   for (int ky = 0; ky < 3; ++ky) {
     const int shift = (ky - 1) * W8;
@@ -274,13 +293,13 @@ __device__ __forceinline__ void issue_tile_pair(bool issuer, uint32_t a_lo_tile,
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk) {
         const uint32_t a_lo = a_lo_tile + (uint32_t)(shift + kk * 2 * Q);
-        const uint32_t b_lo = (b_lo_base + (uint32_t)(3 * ky) * (SLOT_BYTES >> 4) + (uint32_t)(kk * 2 * 128)) | (128u << 16);
+        const uint32_t b_lo = (b_lo_base + (uint32_t)(3 * ky) * (SLOT_BYTES >> 4) + (uint32_t)(kk * 2 * NP)) | ((uint32_t)NP << 16);
         umma_f16(d_tmem, ((uint64_t)DESC_HI << 32) | a_lo, ((uint64_t)DESC_HI << 32) | b_lo, IDESC128, (ky | kk) != 0);
       }
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk) {
         const uint32_t a_lo = a_lo_tile + (uint32_t)(shift - 1 + kk * 2 * Q);
-        const uint32_t b_lo = (b_lo_base + (uint32_t)(3 * ky + 2) * (SLOT_BYTES >> 4) + (uint32_t)(kk * 2 * 64)) | (64u << 16);
+        const uint32_t b_lo = (b_lo_base + (uint32_t)(3 * ky) * (SLOT_BYTES >> 4) + (uint32_t)LEFT16 + (uint32_t)(kk * 2 * NL)) | ((uint32_t)NL << 16);
         umma_f16(d_tmem, ((uint64_t)DESC_HI << 32) | a_lo, ((uint64_t)DESC_HI << 32) | b_lo, IDESC64, 1u);
       }
       if (last_tile) umma_commit(bar_base + (uint32_t)(N_SLOTS + ky) * 8u);                        // w_empty[ky]
@@ -306,7 +325,7 @@ struct Smem {
   static constexpr int OFF_SLOTS = OFF_STATES + 2 * Ge::NB * 16;   // [2][NB] u32 (states/slots ping-pong per batch)
   static constexpr int OFF_BARS = (OFF_SLOTS + 2 * Ge::NB * 4 + 15) & ~15;
   // barriers: w_full[9], w_empty[9], acc_full[4], act_ready[4], stage_ready[4], acc_full of odd batches [4]
-  static constexpr int OFF_TMEM = OFF_BARS + (2 * N_SLOTS + 4 * Ge::NT + 1) * 8;   // + act0_free
+  static constexpr int OFF_TMEM = OFF_BARS + (2 * N_SLOTS + 5 * Ge::NT + 1) * 8;   // + act0_free, head_drained[4]
   static constexpr int TOTAL = OFF_TMEM + 16;
 };
 
@@ -357,6 +376,9 @@ k_eval_umma(const uint8_t* __restrict__ image, const PState* __restrict__ states
   auto bar_stage_ready = [&](int t) { return bar_base + (uint32_t)(2 * N_SLOTS + 2 * Ge::NT + t) * 8u; };
   // activation buffer 0 is free for the next batch's input once every MMA of layer 8 has completed (committed by the MMA warp)
   const uint32_t bar_act0_free = bar_base + (uint32_t)(2 * N_SLOTS + 4 * Ge::NT) * 8u;
+  // the head conv's accumulators (columns 0..95 of a tile) overlap the next batch's stem accumulators (64..127):
+  // the stem MMAs of tile t wait until the head epilogue has read tile t
+  auto bar_head_drained = [&](int t) { return bar_base + (uint32_t)(2 * N_SLOTS + 4 * Ge::NT + 1 + t) * 8u; };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + Sm::OFF_TMEM);
 
   // ---- one-time setup -----------------------------------------------------------------------------
@@ -373,6 +395,7 @@ k_eval_umma(const uint8_t* __restrict__ image, const PState* __restrict__ states
     for (int s = 0; s < N_SLOTS; ++s) { mbar_init(bar_w_full(s), 1); mbar_init(bar_w_empty(s), 1); }
     for (int t = 0; t < Ge::NT; ++t) { mbar_init(bar_acc_full(0, t), 1); mbar_init(bar_acc_full(1, t), 1); mbar_init(bar_act_ready(t), 256); mbar_init(bar_stage_ready(t), 32); }
     mbar_init(bar_act0_free, 1);
+    for (int t = 0; t < Ge::NT; ++t) mbar_init(bar_head_drained(t), 256);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
@@ -403,8 +426,12 @@ k_eval_umma(const uint8_t* __restrict__ image, const PState* __restrict__ states
           for (int g = 0; g < 3; ++g) {                            // one full/empty barrier pair per kernel row = 3 ring slots
             if (use > 0) mbar_wait(bar_w_empty(g), (use - 1) & 1u);
             mbar_expect_tx(bar_w_full(g), 3 * bytes);
-            for (int s = 3 * g; s < 3 * g + 3; ++s)
-              bulk_g2s(s_base + Sm::OFF_W + (uint32_t)s * SLOT_BYTES, src + (size_t)s * bytes, bytes, bar_w_full(g));
+            if (l == 9) {                                          // head: the row's pair + left blocks are one contiguous 18 KB run
+              bulk_g2s(s_base + Sm::OFF_W + (uint32_t)(3 * g) * SLOT_BYTES, src + (size_t)(3 * g) * bytes, 3 * bytes, bar_w_full(g));
+            } else {
+              for (int s = 3 * g; s < 3 * g + 3; ++s)
+                bulk_g2s(s_base + Sm::OFF_W + (uint32_t)s * SLOT_BYTES, src + (size_t)s * bytes, bytes, bar_w_full(g));
+            }
           }
           ++use;
         }
@@ -420,9 +447,13 @@ k_eval_umma(const uint8_t* __restrict__ image, const PState* __restrict__ states
       uint32_t use = 0;        // layer-uses of the weight ring so far
       uint32_t act_par = 0;    // bit t: parity of the next completion of act_ready[t]
       uint32_t stage_par = 0;  // same for stage_ready[t]
+      uint32_t head_par = 0;   // bit t: parity of the completion of head_drained[t] by the PREVIOUS batch
+      int prev_nt = 0;
       for (uint32_t b = 0; b < n_batches; ++b) {
         const uint32_t nb = min((uint32_t)Ge::NB, my_end - my_begin - b * Ge::NB);
         const int nt = (int)((nb * Ge::BS + 127) / 128);
+        const uint32_t hp = head_par;                               // parities of the previous batch's head_drained completions
+        head_par ^= (1u << prev_nt) - 1u;
         for (int l = 0; l < N_LAYERS; ++l) {
           const uint32_t in_buf = s_base + ((l == 0 || (l >= 2 && (l & 1) == 0)) ? Sm::OFF_ACT0 : Sm::OFF_ACT1);
           const uint32_t a_lo_base = ((in_buf >> 4) + Ge::LEAD) | ((uint32_t)Ge::Q << 16);
@@ -437,6 +468,7 @@ k_eval_umma(const uint8_t* __restrict__ image, const PState* __restrict__ states
             if (l == 0) {
               const int wt = min(t + 1, nt - 1);
               mbar_wait(bar_stage_ready(wt), (cur_par >> wt) & 1u);
+              if (t < prev_nt) mbar_wait(bar_head_drained(t), (hp >> t) & 1u);   // the previous batch's head tile t has been read
             } else {
               if (t == 0) mbar_wait(bar_act_ready(0), cur_par & 1u);
               if (t + 1 < nt) { mid_bar = bar_act_ready(t + 1); mid_par = (cur_par >> (t + 1)) & 1u; }
@@ -451,9 +483,9 @@ k_eval_umma(const uint8_t* __restrict__ image, const PState* __restrict__ states
             if (l == 0)
               issue_tile<Ge::W8, Ge::Q, 1, 64>(issuer, a_lo_tile, b_lo_base, 2048 >> 4, d_tmem, first, last, use & 1u, bar_base, 0u, 0u);
             else if (l < 9)
-              issue_tile_pair<Ge::W8, Ge::Q>(issuer, a_lo_tile, b_lo_base, d_tmem, first, last, use & 1u, bar_base, mid_bar, mid_par);
+              issue_tile_pair<Ge::W8, Ge::Q, 128, 64, 1024>(issuer, a_lo_tile, b_lo_base, d_tmem, first, last, use & 1u, bar_base, mid_bar, mid_par);
             else
-              issue_tile<Ge::W8, Ge::Q, 4, HEAD_N>(issuer, a_lo_tile, b_lo_base, SLOT_BYTES >> 4, d_tmem, first, last, use & 1u, bar_base, mid_bar, mid_par);
+              issue_tile_pair<Ge::W8, Ge::Q, 2 * HEAD_N, HEAD_N, 768>(issuer, a_lo_tile, b_lo_base, d_tmem, first, last, use & 1u, bar_base, mid_bar, mid_par);
             if (issuer) {
               umma_commit(bar_acc_full(b & 1u, t));
               if (l == 8 && last) umma_commit(bar_act0_free);
@@ -463,6 +495,7 @@ k_eval_umma(const uint8_t* __restrict__ image, const PState* __restrict__ states
           }
           ++use;
         }
+        prev_nt = nt;
       }
     }
   } else if (warp == STAGER_WARP) {
@@ -610,11 +643,22 @@ k_eval_umma(const uint8_t* __restrict__ image, const PState* __restrict__ states
         tc_fence_after();
         if (et == 0) TRACE(2, bb, 9, t);
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)t * 128u;
-        uint32_t a[16], av[16];
+        // columns [0,48) = D (centre + left taps), [48,96) = E (right tap, one row early): out[r] = D[r] + E[r+1]
+        uint32_t a[16], av[16], e[16], ev[16];
         tmem_ld16(taddr + (uint32_t)half * 16u, a);
-        if (half == 1) tmem_ld16(taddr + 32u, av);
+        tmem_ld16(taddr + (uint32_t)HEAD_N + (uint32_t)half * 16u, e);
+        if (half == 1) { tmem_ld16(taddr + 32u, av); tmem_ld16(taddr + (uint32_t)HEAD_N + 32u, ev); }
         tmem_ld_wait();
         tc_fence_before();
+        mbar_arrive(bar_head_drained(t));                           // the next batch's stem may overwrite columns 64..127 of this tile
+#pragma unroll
+        for (int q = 0; q < 16; ++q)
+          a[q] = __float_as_uint(__uint_as_float(a[q]) + __uint_as_float(__shfl_down_sync(0xffffffffu, e[q], 1)));
+        if (half == 1) {                                            // warp-uniform: half is a property of the warp
+#pragma unroll
+          for (int q = 0; q < 3; ++q)
+            av[q] = __float_as_uint(__uint_as_float(av[q]) + __uint_as_float(__shfl_down_sync(0xffffffffu, ev[q], 1)));
+        }
         if (valid) {
           uint8_t* prow = smem + Sm::OFF_ACT0 + (size_t)(Ge::LEAD + m) * 16;
 #pragma unroll

@@ -88,8 +88,26 @@ static void pack_t(const HostNet& net, std::vector<uint8_t>* out) {
             for (int n = 0; n < 32; ++n)
               left[((size_t)(k / 8) * 32 + n) * 8 + (k % 8)] = f2bf(cv.w[((size_t)(rank * 32 + n) * cv.ic + k) * 9 + ky * 3 + 0]);
           }
+        } else if (l == 9) {
+          // fused head conv in the same kx-pair form: pair half [8 chunks][48 n][8] (rank 0 = centre tap, rank 1 = right
+          // tap; 32 policy + 3 value + 13 zero channels), then the left-tap half [8 chunks][24 n][8] (channels 24*rank ..)
+          uint16_t* left = grp + 8 * HEAD_N * 8;
+          for (int k = 0; k < 64; ++k) {
+            for (int n = 0; n < NET_POLICY_CH + NET_VALUE_CH; ++n) {
+              const HostNet::Conv& cv = n < NET_POLICY_CH ? net.conv[9] : net.conv[10];
+              const int oc = n < NET_POLICY_CH ? n : n - NET_POLICY_CH;
+              grp[((size_t)(k / 8) * HEAD_N + n) * 8 + (k % 8)] = f2bf(cv.w[((size_t)oc * cv.ic + k) * 9 + ky * 3 + (rank == 0 ? 1 : 2)]);
+            }
+            for (int n = 0; n < HEAD_N / 2; ++n) {
+              const int gn = rank * (HEAD_N / 2) + n;
+              if (gn >= NET_POLICY_CH + NET_VALUE_CH) continue;
+              const HostNet::Conv& cv = gn < NET_POLICY_CH ? net.conv[9] : net.conv[10];
+              const int oc = gn < NET_POLICY_CH ? gn : gn - NET_POLICY_CH;
+              left[((size_t)(k / 8) * (HEAD_N / 2) + n) * 8 + (k % 8)] = f2bf(cv.w[((size_t)oc * cv.ic + k) * 9 + ky * 3 + 0]);
+            }
+          }
         } else {
-          // stem / head: three taps, each [KC chunks][NH n][8] with this rank's half of the output channels
+          // stem: three taps, each [KC chunks][NH n][8] with this rank's half of the output channels
           const int NH = layer_n(l) / 2;
           for (int kx = 0; kx < 3; ++kx) {
             uint16_t* blk = grp + (size_t)kx * KC * NH * 8;
@@ -265,7 +283,8 @@ constexpr int BAR_ACT_READY = 22;      // [4] leader only: both CTAs' epilogue w
 constexpr int BAR_STAGE_READY = 26;    // [4] leader only: both CTAs' stagers wrote the tile (count 2)
 constexpr int BAR_ACC_FULL1 = 30;      // [4] odd batches
 constexpr int BAR_ACT0_FREE = 34;
-constexpr int N_BARS = 35;
+constexpr int BAR_HEAD_DRAINED = 35;   // [4] leader only: both CTAs' head epilogues have read the tile (count 16)
+constexpr int N_BARS = 39;
 
 // Stem / head conv of one tile pair: 9 taps x KSTEPS MMAs (M = 256, N output channels, each CTA holds N/2 weight rows).
 // Ring group (3*half + ky) holds the three taps of kernel row ky back to back.
@@ -309,12 +328,15 @@ __device__ __forceinline__ void issue_tile(bool issuer, uint32_t a_lo_tile, uint
 // Residual conv, kx-pair form on a CTA pair: per kernel row ky 4 MMAs of N=128 (centre | right taps: this CTA's ring
 // group starts with its 64 rows of that operand — rank 0 the centre tap, rank 1 the right tap) and 4 MMAs of N=64
 // (left tap, 32 rows per CTA, A shifted one row further back).
-template <int W8, int Q>
+// NP / NL = widths of the pair operand and of the left tap (128 / 64 residual, 96 / 48 head); every CTA holds half of each.
+template <int W8, int Q, int NP, int NL>
 __device__ __forceinline__ void issue_tile_pair(bool issuer, uint32_t a_lo_tile, uint32_t ring_lo, uint32_t half, uint32_t d_tmem,
                                                 bool first_tile, bool last_tile, uint32_t w_par, uint32_t bar_base,
                                                 uint32_t mid_bar, uint32_t mid_par) {
   constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);
-  constexpr uint32_t IDESC128 = make_idesc2(128), IDESC64 = make_idesc2(64);
+  constexpr uint32_t IDESC128 = make_idesc2(NP), IDESC64 = make_idesc2(NL);
+  constexpr uint32_t PH = NP / 2, LH = NL / 2;                    // rows of B per CTA
+  constexpr uint32_t LEFT16 = 8u * PH;                            // the left-tap half follows the pair half (8 chunks x PH rows x 16 B)
 #pragma unroll
   for (int ky = 0; ky < 3; ++ky) {
     const int shift = (ky - 1) * W8;
@@ -333,13 +355,13 @@ __device__ __forceinline__ void issue_tile_pair(bool issuer, uint32_t a_lo_tile,
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk) {
         const uint32_t a_lo = a_lo_tile + (uint32_t)(shift + kk * 2 * Q);
-        const uint32_t b_lo = (g_lo + (uint32_t)(kk * 2 * 64)) | (64u << 16);
+        const uint32_t b_lo = (g_lo + (uint32_t)kk * 2u * PH) | (PH << 16);
         umma2_f16(d_tmem, ((uint64_t)DESC_HI << 32) | a_lo, ((uint64_t)DESC_HI << 32) | b_lo, IDESC128, (ky | kk) != 0);
       }
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk) {
         const uint32_t a_lo = a_lo_tile + (uint32_t)(shift - 1 + kk * 2 * Q);
-        const uint32_t b_lo = (g_lo + (8192u >> 4) + (uint32_t)(kk * 2 * 32)) | (32u << 16);
+        const uint32_t b_lo = (g_lo + LEFT16 + (uint32_t)kk * 2u * LH) | (LH << 16);
         umma2_f16(d_tmem, ((uint64_t)DESC_HI << 32) | a_lo, ((uint64_t)DESC_HI << 32) | b_lo, IDESC64, 1u);
       }
       if (last_tile && ky == 2) umma2_commit(bar_base + (BAR_W_EMPTY + half) * 8u);
@@ -437,6 +459,7 @@ k_eval_umma(const uint8_t* __restrict__ image, const PState* __restrict__ states
     for (int g = 0; g < N_GROUPS; ++g) { mbar_init(bar_w_full_local(g), 1); mbar_init(bar_base + (uint32_t)(BAR_W_FULL_PAIR + g) * 8u, 1); mbar_init(bar_w_empty(g), 1); }
     for (int t = 0; t < Ge::NT; ++t) { mbar_init(bar_acc_full(0, t), 1); mbar_init(bar_acc_full(1, t), 1); mbar_init(bar_act_ready(t), 16); mbar_init(bar_stage_ready(t), 2); }   // one arrival per warp, both CTAs
     mbar_init(bar_act0_free, 1);
+    for (int t = 0; t < Ge::NT; ++t) mbar_init(bar_base + (uint32_t)(BAR_HEAD_DRAINED + t) * 8u, 16);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc2(smem_u32(tmem_slot), 512);
@@ -482,9 +505,13 @@ k_eval_umma(const uint8_t* __restrict__ image, const PState* __restrict__ states
       uint32_t u = 0;          // layers issued so far (ring half u & 1, fill u >> 1)
       uint32_t act_par = 0;    // bit t: parity of the next completion of act_ready[t]
       uint32_t stage_par = 0;  // same for stage_ready[t]
+      uint32_t head_par = 0;   // bit t: parity of the completion of head_drained[t] by the PREVIOUS batch
+      int prev_nt = 0;
       for (uint32_t b = 0; b < n_batches; ++b) {
         uint32_t b0_, nb_; int nt;
         batch_geom(b, &b0_, &nb_, &nt);
+        const uint32_t hp = head_par;
+        head_par ^= (1u << prev_nt) - 1u;
         for (int l = 0; l < N_LAYERS; ++l, ++u) {
           const uint32_t in_buf = s_base + ((l == 0 || (l >= 2 && (l & 1) == 0)) ? Sm::OFF_ACT0 : Sm::OFF_ACT1);
           const uint32_t a_lo_base = ((in_buf >> 4) + Ge::LEAD) | ((uint32_t)Ge::Q << 16);
@@ -499,6 +526,8 @@ k_eval_umma(const uint8_t* __restrict__ image, const PState* __restrict__ states
             if (l == 0) {
               const int wt = min(t + 1, nt - 1);
               mbar_wait_cluster(bar_stage_ready(wt), (cur_par >> wt) & 1u);
+              // the head conv's accumulators (columns 0..95) overlap the stem's (64..127): wait until both CTAs' head epilogues have read tile t
+              if (t < prev_nt) mbar_wait_cluster(bar_base + (uint32_t)(BAR_HEAD_DRAINED + t) * 8u, (hp >> t) & 1u);
             } else {
               if (t == 0) mbar_wait_cluster(bar_act_ready(0), cur_par & 1u);
               if (t + 1 < nt) { mid_bar = bar_act_ready(t + 1); mid_par = (cur_par >> (t + 1)) & 1u; }
@@ -514,9 +543,9 @@ k_eval_umma(const uint8_t* __restrict__ image, const PState* __restrict__ states
             if (l == 0)
               issue_tile<Ge::W8, Ge::Q, 1, 64>(issuer, a_lo_tile, ring_lo, half, d_tmem, first, last, w_par, bar_base, 0u, 0u);
             else if (l < 9)
-              issue_tile_pair<Ge::W8, Ge::Q>(issuer, a_lo_tile, ring_lo, half, d_tmem, first, last, w_par, bar_base, mid_bar, mid_par);
+              issue_tile_pair<Ge::W8, Ge::Q, 128, 64>(issuer, a_lo_tile, ring_lo, half, d_tmem, first, last, w_par, bar_base, mid_bar, mid_par);
             else
-              issue_tile<Ge::W8, Ge::Q, 4, HEAD_N>(issuer, a_lo_tile, ring_lo, half, d_tmem, first, last, w_par, bar_base, mid_bar, mid_par);
+              issue_tile_pair<Ge::W8, Ge::Q, 2 * HEAD_N, HEAD_N>(issuer, a_lo_tile, ring_lo, half, d_tmem, first, last, w_par, bar_base, mid_bar, mid_par);
             if (issuer) {
               umma2_commit(bar_acc_full(b & 1u, t));
               if (l == 8 && last) umma2_commit(bar_act0_free);
@@ -525,6 +554,7 @@ k_eval_umma(const uint8_t* __restrict__ image, const PState* __restrict__ states
             if (lane == 0) TRACE(1, b, l, t);
           }
         }
+        prev_nt = nt;
       }
     } else if (lane == 0) {
       // peer CTA: tell the leader's MMA warp when THIS CTA's half of a weight group has landed
@@ -687,11 +717,26 @@ k_eval_umma(const uint8_t* __restrict__ image, const PState* __restrict__ states
         tc_fence_after();
         if (et == 0) TRACE(2, bb, 9, t);
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)t * 128u;
-        uint32_t a[16], av[16];
+        // columns [0,48) = D (centre + left taps), [48,96) = E (right tap, one row early): out[r] = D[r] + E[r+1]
+        uint32_t a[16], av[16], e[16], ev[16];
         tmem_ld16(taddr + (uint32_t)half * 16u, a);
-        if (half == 1) tmem_ld16(taddr + 32u, av);
+        tmem_ld16(taddr + (uint32_t)HEAD_N + (uint32_t)half * 16u, e);
+        if (half == 1) { tmem_ld16(taddr + 32u, av); tmem_ld16(taddr + (uint32_t)HEAD_N + 32u, ev); }
         tmem_ld_wait();
         tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {                                            // the next batch's stem may overwrite columns 64..127 of this tile
+          if (rank == 0) mbar_arrive(bar_base + (uint32_t)(BAR_HEAD_DRAINED + t) * 8u);
+          else mbar_arrive_cluster(lead_bar_base + (uint32_t)(BAR_HEAD_DRAINED + t) * 8u);
+        }
+#pragma unroll
+        for (int q = 0; q < 16; ++q)
+          a[q] = __float_as_uint(__uint_as_float(a[q]) + __uint_as_float(__shfl_down_sync(0xffffffffu, e[q], 1)));
+        if (half == 1) {                                            // warp-uniform: half is a property of the warp
+#pragma unroll
+          for (int q = 0; q < 3; ++q)
+            av[q] = __float_as_uint(__uint_as_float(av[q]) + __uint_as_float(__shfl_down_sync(0xffffffffu, ev[q], 1)));
+        }
         if (valid) {
           uint8_t* prow = smem + Sm::OFF_ACT0 + (size_t)(Ge::LEAD + m) * 16;
 #pragma unroll
