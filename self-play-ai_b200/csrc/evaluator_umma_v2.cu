@@ -9,8 +9,9 @@
 // (columns 64..127, right tap, computed one row early).  The left tap (kx = -1) stays a N=64 MMA with A shifted by
 // one row, accumulating into D.  24 MMAs per tile-layer instead of 36; the epilogue forms out[r] = D[r] + E[r+1]
 // with one warp shuffle per channel — row r+1 of lane 31 is never needed because rows 32k-1 are pad cells.
-// Accumulators: 128 TMEM columns per tile, 4 tiles = 512 columns; the stem of the next batch accumulates in the E
-// half (free while the head conv uses D), which keeps v1's overlap of batch b+1's stem with batch b's head.
+// The fused head conv has the same form (N = 96 + 48).  Accumulators: 128 TMEM columns per tile, 4 tiles = 512 columns; the
+// stem of the next batch accumulates in columns 64..127 of a tile once the head epilogue has read that tile (head_drained),
+// which keeps the overlap of batch b+1's stem with batch b's head.
 #include <cuda_bf16.h>
 
 #include <cstring>
@@ -476,8 +477,8 @@ k_eval_umma(const uint8_t* __restrict__ image, const PState* __restrict__ states
             tc_fence_after();
             if (lane == 0) TRACE(0, b, l, t);
             const uint32_t a_lo_tile = a_lo_base + (uint32_t)t * 128u;
-            // 128 columns per tile: D = [0,64) and E = [64,128).  The stem accumulates in the E half, which is idle
-            // while the head conv of the previous batch still owns D.
+            // 128 columns per tile: D = [0,64) and E = [64,128) (head conv: [0,48) and [48,96)).  The stem accumulates in
+            // columns 64..127; the head_drained wait above keeps it off the previous batch's head columns.
             const uint32_t d_tmem = tmem_base + (uint32_t)t * 128u + (l == 0 ? 64u : 0u);
             const bool first = (t == 0), last = (t == nt - 1);
             if (l == 0)

@@ -535,8 +535,8 @@ k_eval_umma(const uint8_t* __restrict__ image, const PState* __restrict__ states
             tc_fence_after();
             if (lane == 0) TRACE(0, b, l, t);
             const uint32_t a_lo_tile = a_lo_base + (uint32_t)t * 128u;
-            // 128 columns per tile: D = [0,64) and E = [64,128).  The stem accumulates in the E half, which is idle
-            // while the head conv of the previous batch still owns D.
+            // 128 columns per tile: D = [0,64) and E = [64,128) (head conv: [0,48) and [48,96)).  The stem accumulates in
+            // columns 64..127; the head_drained wait above keeps it off the previous batch's head columns.
             const uint32_t d_tmem = tmem_base + (uint32_t)t * 128u + (l == 0 ? 64u : 0u);
             const bool first = (t == 0), last = (t == nt - 1);
             const uint32_t half = u & 1u, w_par = (u >> 1) & 1u;
