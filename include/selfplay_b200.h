@@ -255,8 +255,9 @@ int32_t spb_drain_trajectories(spb_engine* e, spb_position* buf, size_t capacity
 int32_t spb_get_counters(spb_engine* e, spb_counters* out);
 int32_t spb_reset_counters(spb_engine* e);
 /*
- * Device time (CUDA events on the engine's stream) of the most recent spb_search,
- * and of the evaluator kernel launches inside it (sum, count).
+ * Device time (CUDA events on the engine's stream) of the most recent spb_search and the number of evaluator
+ * launches inside it.  evaluator_ms is reserved and reads 0: the steps run as one CUDA graph of programmatically
+ * dependent launches, so there is no per-launch event — spb_time_evaluator measures the evaluator's launch time.
  */
 int32_t spb_last_search_timing(spb_engine* e, float* search_ms, float* evaluator_ms,
                                uint32_t* evaluator_launches);
