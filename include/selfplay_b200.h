@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define SPB_ABI_VERSION 1
+#define SPB_ABI_VERSION 2
 
 /* ---- status codes ------------------------------------------------------- */
 #define SPB_OK             0
@@ -91,19 +91,21 @@ typedef struct spb_config {
   uint32_t flags;                /* SPB_FLAG_* */
   uint32_t game_id_base;         /* id of slot 0's first self-play game (rank offset when games are sharded over GPUs) */
   uint32_t game_id_stride;       /* id increment when a slot starts its next game; 0 = num_games */
-  uint32_t reserved[5];          /* must be zero */
+  uint32_t trajectory_capacity;  /* records of the finished-trajectory buffer drained by spb_drain_trajectories;
+                                    0 = default (4 * num_games * max plies, at most 2^26) */
+  uint32_t reserved[4];          /* must be zero */
 } spb_config;
 
 #define SPB_FLAG_NO_GRAPH   1u   /* launch kernels directly instead of through a CUDA graph */
 #define SPB_FLAG_EVAL_SIMT  2u   /* use the CUDA-core evaluator kernel instead of tcgen05 (debug / cross-check) */
-#define SPB_FLAG_EVAL_V1    32u  /* use the first tcgen05 evaluator kernel (one MMA group per 3x3 tap, N = 64) instead of the default
-                                    kx-pair kernel (centre + right taps share one A fetch, N = 128): cross-check / A-B timing */
-#define SPB_FLAG_EVAL_PAIR2 64u  /* tcgen05 evaluator on CTA pairs (cta_group::2): experimental */
+#define SPB_FLAG_LOCKSTEP   32u  /* network evaluator: run the reference's loop literally — per simulation step one evaluator
+                                    launch for the leaves of all trees, then one tree-step launch (mcts.rs:214-286) — instead of
+                                    the asynchronous pipeline, whose results are bit-identical */
 #define SPB_FLAG_FIXED_POOL 16u  /* never grow the node pools: a tree that would pass max_nodes_per_tree makes spb_search return
                                     SPB_ERR_POOL.  Without the flag the pools grow before a search that could outgrow them, like
                                     the reference's Vec arena (mcts.rs:19) */
-#define SPB_FLAG_FORCE_SPLIT 4u  /* run DetEval / uniform through the lock-step select -> evaluate -> expand pipeline
-                                    of the network evaluator instead of the fused single-kernel search */
+#define SPB_FLAG_FORCE_SPLIT 4u  /* run DetEval / uniform through the pipeline of the network evaluator (asynchronous, or lock-step
+                                    with SPB_FLAG_LOCKSTEP) instead of the fused single-kernel search: parity harness */
 
 typedef struct spb_engine spb_engine;
 
@@ -242,7 +244,10 @@ typedef struct spb_position {
  * game (terminal child: emit the trajectory with outcomes, restart the slot from
  * a fresh root if `restart_roots` != NULL, else leave it idle) or re-root
  * (use_subtree).  `seed` feeds the counter-based RNG of SPB_MOVE_TEMPERATURE.
- * n_finished (nullable) receives the number of games that ended in this call.
+ * n_finished (nullable) receives the number of games whose trajectory was emitted in this call.
+ * When the trajectory buffer cannot take a finished game the call returns SPB_ERR_STATE: nothing is lost or
+ * half-written — the game's slot is parked (idle, skipped by spb_search) with its history kept; drain with
+ * spb_drain_trajectories and carry on: the next spb_selfplay_step emits the parked games first.
  */
 int32_t spb_selfplay_step(spb_engine* e, int32_t rule, float temperature, uint64_t seed,
                           const spb_state* restart_roots, uint32_t* n_finished);
@@ -262,6 +267,12 @@ int32_t spb_reset_counters(spb_engine* e);
 int32_t spb_last_search_timing(spb_engine* e, float* search_ms, float* evaluator_ms,
                                uint32_t* evaluator_launches);
 int32_t spb_synchronize(spb_engine* e);
+/*
+ * Statistics of the most recent search through the asynchronous pipeline (zeros for the other pipelines), out[0..n):
+ * [0] evaluator batches, [1] boards in them, [2] ns the evaluator CTAs waited for leaves (sum over CTAs), [3] ns the tree
+ * warps spent on trees (sum over warps), [4] tree visits, [5] tree warps, [6] evaluator CTAs.
+ */
+int32_t spb_last_async_stats(spb_engine* e, uint64_t* out, uint32_t n);
 /*
  * Re-runs the evaluator kernel `iters` times on the work list of the most recent lock-step search (the leaves of
  * its last simulation step, still resident in HBM) and reports the average launch duration, measured with CUDA

@@ -1,9 +1,9 @@
-//! 1:1 mirror of `include/selfplay_b200.h` (ABI version 1).  NOT compiled in the build image
+//! 1:1 mirror of `include/selfplay_b200.h` (ABI version 2).  NOT compiled in the build image
 //! (no rustc/cargo there); kept line-for-line with the header so it can be checked by eye.
 #![allow(non_camel_case_types)]
 use std::os::raw::{c_char, c_void};
 
-pub const SPB_ABI_VERSION: u32 = 1;
+pub const SPB_ABI_VERSION: u32 = 2;
 pub const SPB_OK: i32 = 0;
 pub const SPB_ERR_ARG: i32 = -1;
 pub const SPB_ERR_CUDA: i32 = -2;
@@ -24,8 +24,7 @@ pub const SPB_EVAL_UNIFORM: i32 = 2;
 pub const SPB_FLAG_NO_GRAPH: u32 = 1;
 pub const SPB_FLAG_EVAL_SIMT: u32 = 2;
 pub const SPB_FLAG_FORCE_SPLIT: u32 = 4;
-pub const SPB_FLAG_EVAL_V1: u32 = 32;
-pub const SPB_FLAG_EVAL_PAIR2: u32 = 64;
+pub const SPB_FLAG_LOCKSTEP: u32 = 32;
 pub const SPB_FLAG_FIXED_POOL: u32 = 16;
 pub const SPB_MOVE_GREEDY_LAST_MAX: i32 = 0;
 pub const SPB_MOVE_TEMPERATURE: i32 = 1;
@@ -54,7 +53,8 @@ pub struct spb_config {
     pub flags: u32,
     pub game_id_base: u32,
     pub game_id_stride: u32,
-    pub reserved: [u32; 5],
+    pub trajectory_capacity: u32,
+    pub reserved: [u32; 4],
 }
 
 #[repr(C)]

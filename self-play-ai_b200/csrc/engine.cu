@@ -16,6 +16,7 @@
 
 #include <cuda_runtime.h>
 
+#include "async.cuh"
 #include "evaluator.cuh"
 #include "tree.cuh"
 
@@ -31,13 +32,14 @@ namespace spb {
   } while (0)
 
 constexpr int WARPS_PER_BLOCK = 4;
+constexpr int CTL_WORDS = 9 * 32;   // control words of the asynchronous pipeline, one 128-byte line each
 constexpr int THREADS = WARPS_PER_BLOCK * 32;
 
 // ------------------------------------------------------------------------------------------------
 // kernels
 // ------------------------------------------------------------------------------------------------
 
-__global__ void k_reset(Trees T, uint32_t* hist_len, const uint32_t* slots, const PState* roots, uint32_t n) {
+__global__ void k_reset(Trees T, uint32_t* hist_len, uint8_t* parked, const uint32_t* slots, const PState* roots, uint32_t n) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   uint32_t g = slots ? slots[i] : i;
@@ -46,6 +48,7 @@ __global__ void k_reset(Trees T, uint32_t* hist_len, const uint32_t* slots, cons
   T.buf[g] = 0;
   T.live[g] = 1;
   T.n_nodes[g] = 1;
+  parked[g] = 0;
   hist_len[g] = 0;   // a restarted slot starts a new trajectory (Tree::with_root_state has empty histories, mcts.rs:86-89)
   NodeRec r;
   r.N = 0; r.W = 0.0f; r.P = 0.0f;
@@ -53,14 +56,6 @@ __global__ void k_reset(Trees T, uint32_t* hist_len, const uint32_t* slots, cons
   T.rec[0][(size_t)g * T.cap] = r;
   T.par[0][(size_t)g * T.cap] = PAR_NONE | (0xFFu << 24);
   for (uint32_t k = 0; k < T.K; ++k) T.leaf_info[g * T.K + k] = 0;
-}
-
-__device__ __forceinline__ void flush_counters(const Trees& T, const unsigned long long* local, int lane) {
-  if (lane == 0) {
-#pragma unroll
-    for (int i = 0; i < CTR_COUNT; ++i)
-      if (local[i]) atomicAdd(&T.counters[i], local[i]);
-  }
 }
 
 // Fused search: all simulations of one tree inside one warp, evaluator in registers.
@@ -161,7 +156,7 @@ __global__ void __launch_bounds__(THREADS) k_tree_step(Trees T, int do_finish, i
   for (int a = 0; a < G::A; ++a) probs[a] = eo[a];
   const float v = eo[G::A];
   uint32_t n_nodes = T.n_nodes[g];
-  const uint32_t pn0 = pathm[lane];
+  const uint32_t pn0 = (lane < G::MAX_DEPTH) ? pathm[lane] : 0u;   // tic-tac-toe paths are 12 words: lanes beyond must not read the next slot's
   const uint32_t pn1 = (lane + 32 < G::MAX_DEPTH) ? pathm[lane + 32] : 0u;
   if (!live) return;
 #ifdef SPB_TRACE
@@ -367,6 +362,26 @@ __global__ void k_eval_builtin(const PState* states, const uint32_t* list, const
   o[G::A] = v;
 }
 
+// ---- asynchronous pipeline (async.cuh) --------------------------------------------------------------------
+// Start of a search: every live tree gets its simulation budget and a ticket of the ready ring.
+__global__ void k_async_init(Trees T, AsyncCtl C, uint32_t num_searches) {
+  const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= T.G || !T.live[g]) return;
+  C.sims_left[g] = num_searches;
+  atomicAdd(C.n_active, 1u);
+  const uint32_t t = atomicAdd(C.ready.tail, 1u);
+  C.ready.slots[t & C.ready.mask] = ring_entry(t, g);
+}
+
+// The pipeline with the built-in evaluators (parity harness: SPB_FLAG_FORCE_SPLIT): the same rings and tree warps as the
+// network pipeline, evaluator CTAs replaced by evaluator warps.  Warps 0,1 evaluate, warps 2,3 own trees.
+template <class G, int EVAL>
+__global__ void __launch_bounds__(THREADS) k_async_builtin(Trees T, AsyncCtl C) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (warp < 2) builtin_eval_worker<G, EVAL>(T, C, gridDim.x * 2u, lane);
+  else tree_worker<G>(T, C, lane);
+}
+
 // Replays the moves from the root to `node` (walks the parent links up, then down again).
 template <class G>
 __device__ PState node_state(const Trees& T, uint32_t g, uint32_t node) {
@@ -529,6 +544,8 @@ __global__ void k_mask_policies(const PState* states, uint32_t n, const float* e
 struct SelfPlay {
   spb_position* hist;        // [G][MAX_PLY]
   uint32_t* hist_len;        // [G]
+  uint8_t* parked;           // [G]  0, or 1 | terminal status << 1 | terminal side to move << 3: the game has ended but its trajectory
+                             //      did not fit the output buffer; the slot is idle until the next spb_selfplay_step emits it
   unsigned long long* game_id;     // [G]
   spb_position* out;         // [out_cap]
   unsigned long long* out_game;    // [out_cap]
@@ -540,12 +557,73 @@ struct SelfPlay {
 };
 enum : uint32_t { ERRBIT_TRAJ_FULL = 4u };
 
+// Reserves `plies` records of the trajectory output buffer (lane 0; all lanes get the answer).  The cursor only moves
+// when the whole trajectory fits, so every record below the cursor is fully written: a drain never sees a hole.
+__device__ __forceinline__ bool reserve_output(const SelfPlay& P, uint32_t plies, int lane, unsigned long long* base_out) {
+  unsigned long long base = ~0ull;
+  if (lane == 0) {
+    unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(P.out_cursor);
+    for (;;) {
+      if (cur + plies > P.out_cap) { base = ~0ull; break; }
+      const unsigned long long seen = atomicCAS(P.out_cursor, cur, cur + plies);
+      if (seen == cur) { base = cur; break; }
+      cur = seen;
+    }
+  }
+  base = __shfl_sync(0xffffffffu, base, 0);
+  *base_out = base;
+  return base != ~0ull;
+}
+
+// Emits the finished game of slot g (learner_concurrent.rs:200-230) and restarts or retires the slot.
+__device__ __forceinline__ void emit_and_finish(const Trees& T, const SelfPlay& P, uint32_t g, uint32_t plies, uint32_t cstatus,
+                                                uint32_t term_player, unsigned long long base, const PState* restart_roots, int lane) {
+  const float value = terminal_value(cstatus);                     // from the terminal state's side to move
+  for (uint32_t i = lane; i < plies; i += 32) {
+    spb_position p = P.hist[(size_t)g * P.max_ply + i];
+    float v = (p.current_player == term_player) ? value : -value;   // :214-226
+    p.outcome = (int8_t)v;
+    P.out[base + i] = p;
+    P.out_game[base + i] = P.game_id[g];
+  }
+  __syncwarp();
+  if (lane == 0) {
+    atomicAdd(P.finished, 1u);
+    P.hist_len[g] = 0;
+    P.parked[g] = 0;
+    P.game_id[g] += P.id_stride;
+    if (restart_roots) {                                           // Tree::with_root_state for the next game
+      PState nr = restart_roots[g];
+      T.root_state[g] = nr;
+      T.buf[g] = 0;
+      T.n_nodes[g] = 1;
+      T.live[g] = 1;
+      NodeRec r; r.N = 0; r.W = 0.0f; r.P = 0.0f; r.info = make_info(0, 0, ps_status(nr));
+      T.rec[0][(size_t)g * T.cap] = r;
+      T.par[0][(size_t)g * T.cap] = PAR_NONE | (0xFFu << 24);
+      for (uint32_t k = 0; k < T.K; ++k) T.leaf_info[g * T.K + k] = 0;
+    } else {
+      T.live[g] = 0;                                               // trees_vec.remove(i), :230
+    }
+  }
+}
+
 template <class G>
 __global__ void __launch_bounds__(THREADS) k_selfplay_step(Trees T, SelfPlay P, int rule, float temperature,
                                                            unsigned long long seed, const PState* restart_roots) {
   const int lane = threadIdx.x & 31;
   const uint32_t g = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
-  if (g >= T.G || !T.live[g]) return;
+  if (g >= T.G) return;
+  const uint32_t pk = P.parked[g];
+  if (pk) {
+    // A game that ended in an earlier call while the output buffer was full: the slot has been idle since; emit now.
+    const uint32_t plies = P.hist_len[g];
+    unsigned long long base;
+    if (reserve_output(P, plies, lane, &base)) emit_and_finish(T, P, g, plies, (pk >> 1) & 3u, (pk >> 3) & 1u, base, restart_roots, lane);
+    else if (lane == 0) atomicOr(T.error, ERRBIT_TRAJ_FULL);
+    return;
+  }
+  if (!T.live[g]) return;
   const uint32_t b = T.buf[g];
   NodeRec* rec = T.rec[b] + (size_t)g * T.cap;
   const uint32_t* par = T.par[b] + (size_t)g * T.cap;
@@ -591,45 +669,21 @@ __global__ void __launch_bounds__(THREADS) k_selfplay_step(Trees T, SelfPlay P, 
     __syncwarp();
   }
   const uint32_t cstatus = info_status(__shfl_sync(0xffffffffu, cinfo, chosen));
-  const uint32_t cact = __shfl_sync(0xffffffffu, act, chosen);
   const uint32_t plies = min(ply + 1, P.max_ply);
   if (cstatus != SPB_STATUS_ONGOING) {
-    // learner_concurrent.rs:200-230: emit the trajectory; value is from the terminal state's side to move.
-    const float value = terminal_value(cstatus);
+    // learner_concurrent.rs:200-230: the game is over.  The trajectory is emitted only when all of it fits the output
+    // buffer; otherwise the slot is parked (idle, history kept) and the call reports SPB_ERR_STATE: the caller drains
+    // and the next spb_selfplay_step emits the parked games, so no game and no record is ever lost or half-written.
     const uint32_t term_player = ps_player(root) ^ 1u;
-    unsigned long long base = 0;
-    if (lane == 0) base = atomicAdd(P.out_cursor, (unsigned long long)plies);
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (base + plies <= P.out_cap) {
-      for (uint32_t i = lane; i < plies; i += 32) {
-        spb_position p = P.hist[(size_t)g * P.max_ply + i];
-        float v = (p.current_player == term_player) ? value : -value;   // :214-226
-        p.outcome = (int8_t)v;
-        P.out[base + i] = p;
-        P.out_game[base + i] = P.game_id[g];
-      }
+    unsigned long long base;
+    if (reserve_output(P, plies, lane, &base)) {
+      emit_and_finish(T, P, g, plies, cstatus, term_player, base, restart_roots, lane);
     } else if (lane == 0) {
+      P.hist_len[g] = plies;
+      P.parked[g] = (uint8_t)(1u | (cstatus << 1) | (term_player << 3));
+      T.live[g] = 0;
       atomicOr(T.error, ERRBIT_TRAJ_FULL);
     }
-    __syncwarp();
-    if (lane == 0) {
-      atomicAdd(P.finished, 1u);
-      P.hist_len[g] = 0;
-      P.game_id[g] += P.id_stride;
-      if (restart_roots) {                                       // Tree::with_root_state for the next game
-        PState nr = restart_roots[g];
-        T.root_state[g] = nr;
-        T.buf[g] = 0;
-        T.n_nodes[g] = 1;
-        NodeRec r; r.N = 0; r.W = 0.0f; r.P = 0.0f; r.info = make_info(0, 0, ps_status(nr));
-        T.rec[0][(size_t)g * T.cap] = r;
-        T.par[0][(size_t)g * T.cap] = PAR_NONE | (0xFFu << 24);
-        for (uint32_t k = 0; k < T.K; ++k) T.leaf_info[g * T.K + k] = 0;
-      } else {
-        T.live[g] = 0;                                           // trees_vec.remove(i), :230
-      }
-    }
-    (void)cact;
   } else {
     if (lane == 0) P.hist_len[g] = plies;
     reroot<G>(T, g, fc + (uint32_t)chosen, lane);                // :233-234
@@ -665,6 +719,12 @@ struct spb_engine {
   int last_eval_parity = -1;   // parity of the work list the last evaluator launch of spb_search consumed
   // CUDA graph of one split-pipeline step pair (parity 0 and 1)
   cudaGraphExec_t step_graph = nullptr;
+  // asynchronous pipeline: rings + control words (async.cuh)
+  AsyncCtl ctl{};
+  uint32_t* d_ctl_words = nullptr;   // [CTL_WORDS] one 128-byte line per counter
+  unsigned long long* d_ring_slots = nullptr;   // [2][ring_size]
+  uint32_t ring_size = 0;
+  uint64_t last_async_stats[16] = {};
   int A = 0, max_depth = 0, eval_stride = 0, max_ply = 0;
 
   void set_error(const std::string& s) { err = s; }
@@ -700,6 +760,7 @@ struct spb_engine {
   void destroy();
   template <class G> int32_t search_t(uint32_t num_searches);
   template <class G> int32_t launch_eval_step(uint32_t parity);
+  template <class G> int32_t search_async(uint32_t num_searches);
 };
 
 #define SPB_CHECK_LAUNCH() SPB_CUDA(cudaGetLastError())
@@ -744,12 +805,31 @@ int32_t spb_engine::init() {
   if ((rc = dalloc(&d_rc_ids, G * SPB_MAX_ACTIONS))) return rc;
   if ((rc = dalloc(&d_rc_n, G))) return rc;
   if ((rc = dalloc(&d_misc, 4))) return rc;
+  // asynchronous pipeline: two rings of >= 2G entries (a ring never holds more than G) and the control words
+  {
+    ring_size = 1024;
+    while (ring_size < 2 * (size_t)G) ring_size <<= 1;
+    if ((rc = dalloc(&d_ring_slots, 2 * (size_t)ring_size))) return rc;
+    if ((rc = dalloc(&d_ctl_words, (size_t)CTL_WORDS))) return rc;
+    if ((rc = dalloc(&ctl.sims_left, G))) return rc;
+    ctl.leaf.slots = d_ring_slots;            ctl.leaf.mask = ring_size - 1;
+    ctl.ready.slots = d_ring_slots + ring_size; ctl.ready.mask = ring_size - 1;
+    ctl.leaf.head = d_ctl_words + 0 * 32;  ctl.leaf.tail = d_ctl_words + 1 * 32;
+    ctl.ready.head = d_ctl_words + 2 * 32; ctl.ready.tail = d_ctl_words + 3 * 32;
+    ctl.n_active = d_ctl_words + 4 * 32;   ctl.done_count = d_ctl_words + 5 * 32;
+    ctl.abort = d_ctl_words + 6 * 32;
+    ctl.stats = reinterpret_cast<unsigned long long*>(d_ctl_words + 7 * 32);   // 2 lines: ASTAT_COUNT u64
+    ctl.stall_ns = 2000000000ull;             // 2 s without a single hand-off anywhere: a bug, reported as SPB_ERR_STATE
+    SPB_CUDA(cudaMemsetAsync(ctl.sims_left, 0, G * 4, stream));
+  }
   // self-play buffers
   P.max_ply = (uint32_t)max_ply;
   P.out_cap = (uint32_t)std::min<size_t>(G * max_ply * 4, (size_t)1 << 26);
+  if (cfg.trajectory_capacity) P.out_cap = std::max<uint32_t>(cfg.trajectory_capacity, (uint32_t)max_ply);   // a whole game always fits
   P.id_stride = cfg.game_id_stride ? cfg.game_id_stride : (unsigned long long)G;
   if ((rc = dalloc(&P.hist, G * max_ply))) return rc;
   if ((rc = dalloc(&P.hist_len, G))) return rc;
+  if ((rc = dalloc(&P.parked, G))) return rc;
   if ((rc = dalloc(&P.game_id, G))) return rc;
   if ((rc = dalloc(&P.out, (size_t)P.out_cap))) return rc;
   if ((rc = dalloc(&P.out_game, (size_t)P.out_cap))) return rc;
@@ -759,11 +839,13 @@ int32_t spb_engine::init() {
   SPB_CUDA(cudaMemsetAsync(T.buf, 0, G, stream));
   SPB_CUDA(cudaMemsetAsync(T.n_nodes, 0, G * 4, stream));
   SPB_CUDA(cudaMemsetAsync(T.leaf_info, 0, slots * 4, stream));
+  SPB_CUDA(cudaMemsetAsync(T.leaf_state, 0, slots * sizeof(PState), stream));
   SPB_CUDA(cudaMemsetAsync(T.eval_count, 0, 16, stream));
   SPB_CUDA(cudaMemsetAsync(T.eval_out, 0, slots * eval_stride * 4, stream));
   SPB_CUDA(cudaMemsetAsync(T.counters, 0, CTR_COUNT * 8, stream));
   SPB_CUDA(cudaMemsetAsync(T.error, 0, 4, stream));
   SPB_CUDA(cudaMemsetAsync(P.hist_len, 0, G * 4, stream));
+  SPB_CUDA(cudaMemsetAsync(P.parked, 0, G, stream));
   SPB_CUDA(cudaMemsetAsync(P.out_cursor, 0, 8, stream));
   SPB_CUDA(cudaMemsetAsync(P.finished, 0, 4, stream));
   {
@@ -894,9 +976,15 @@ int32_t spb_engine::search_t(uint32_t num_searches) {
   const bool split = cfg.evaluator == SPB_EVAL_NET || (cfg.flags & SPB_FLAG_FORCE_SPLIT) || T.K > 1;
   if (cfg.evaluator == SPB_EVAL_NET && !evaluator.loaded()) { set_error("no weights loaded: call spb_load_weights first"); return SPB_ERR_STATE; }
   { int32_t rc = ensure_capacity(num_searches); if (rc != SPB_OK) return rc; }
+  // The network evaluator (and the built-in evaluators under SPB_FLAG_FORCE_SPLIT) run through the asynchronous
+  // pipeline unless the lock-step pipeline is asked for; K > 1 leaves per tree is a lock-step extension.
+  const bool async = split && T.K == 1 && !(cfg.flags & SPB_FLAG_LOCKSTEP);
   SPB_CUDA(cudaEventRecord(ev0, stream));
   last_eval_launches = 0;
-  if (!split) {
+  if (async) {
+    int32_t rc = search_async<G>(num_searches);
+    if (rc != SPB_OK) return rc;
+  } else if (!split) {
     if (cfg.evaluator == SPB_EVAL_DET) k_search_fused<G, SPB_EVAL_DET><<<blocks, THREADS, 0, stream>>>(T, num_searches);
     else k_search_fused<G, SPB_EVAL_UNIFORM><<<blocks, THREADS, 0, stream>>>(T, num_searches);
     SPB_CHECK_LAUNCH();
@@ -970,9 +1058,43 @@ int32_t spb_engine::search_t(uint32_t num_searches) {
     }
   }
   SPB_CUDA(cudaEventRecord(ev1, stream));
+  uint32_t ctl_host[CTL_WORDS];
+  if (async) SPB_CUDA(cudaMemcpyAsync(ctl_host, d_ctl_words, sizeof ctl_host, cudaMemcpyDeviceToHost, stream));
   int32_t rc = check_device_errors();   // synchronises the stream
   SPB_CUDA(cudaEventElapsedTime(&last_search_ms, ev0, ev1));
+  if (async) std::memcpy(last_async_stats, &ctl_host[7 * 32], sizeof(uint64_t) * ASTAT_COUNT);
+  if (rc == SPB_OK && async && (ctl_host[6 * 32] != 0u || ctl_host[5 * 32] != ctl_host[4 * 32])) {
+    char msg[256];
+    std::snprintf(msg, sizeof msg, "asynchronous search pipeline stalled (abort=%u, trees done %u of %u, leaf ring %u/%u, ready ring %u/%u)",
+                  ctl_host[6 * 32], ctl_host[5 * 32], ctl_host[4 * 32], ctl_host[0], ctl_host[32], ctl_host[64], ctl_host[96]);
+    set_error(msg);
+    return SPB_ERR_STATE;
+  }
   return rc;
+}
+
+// One search through the asynchronous pipeline: rings reset, every live tree queued, ONE resident kernel until all trees
+// have completed their simulations (network: evaluator CTAs + tree warps; built-in evaluators: evaluator warps + tree warps).
+template <class G>
+int32_t spb_engine::search_async(uint32_t num_searches) {
+  SPB_CUDA(cudaMemsetAsync(d_ctl_words, 0, (size_t)CTL_WORDS * 4, stream));
+  SPB_CUDA(cudaMemsetAsync(d_ring_slots, 0, 2 * (size_t)ring_size * 8, stream));
+  k_async_init<<<(T.G + 127) / 128, 128, 0, stream>>>(T, ctl, num_searches);
+  SPB_CHECK_LAUNCH();
+  ++launches;
+  if (cfg.evaluator == SPB_EVAL_NET) {
+    cudaError_t e = evaluator.launch_ring(T, ctl, stream);
+    if (e != cudaSuccess) { set_error(std::string("evaluator launch: ") + cudaGetErrorString(e)); return SPB_ERR_CUDA; }
+    ++last_eval_launches;
+  } else {
+    const uint32_t grid = std::max(1u, std::min(592u, (T.G + 3u) / 4u));
+    if (cfg.evaluator == SPB_EVAL_DET) k_async_builtin<G, SPB_EVAL_DET><<<grid, THREADS, 0, stream>>>(T, ctl);
+    else k_async_builtin<G, SPB_EVAL_UNIFORM><<<grid, THREADS, 0, stream>>>(T, ctl);
+    SPB_CHECK_LAUNCH();
+  }
+  ++launches;
+  last_eval_parity = -1;
+  return SPB_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1021,8 +1143,6 @@ int32_t spb_create(const spb_config* cfg, spb_engine** out) {
   spb_engine* e = new (std::nothrow) spb_engine();
   if (!e) { g_create_error = "out of host memory"; return SPB_ERR_NOMEM; }
   e->cfg = *cfg;
-  e->evaluator.use_v3((cfg->flags & SPB_FLAG_EVAL_PAIR2) != 0);
-  e->evaluator.use_v1((cfg->flags & SPB_FLAG_EVAL_V1) != 0);   // default: kx-pair kernel (evaluator_umma_v2.cu)
   if (e->cfg.max_nodes_per_tree == 0) e->cfg.max_nodes_per_tree = 16384;
   if (e->cfg.max_nodes_per_tree < 16 || e->cfg.max_nodes_per_tree > MAX_CAP) { g_create_error = "max_nodes_per_tree out of range"; delete e; return SPB_ERR_ARG; }
   int32_t rc = e->init();
@@ -1055,6 +1175,10 @@ int32_t spb_load_weights(spb_engine* e, const void* blob, size_t n) {
   if (!parse_safetensors_net(blob, n, e->cfg.game, &net, &err)) { e->set_error("spb_load_weights: " + err); return SPB_ERR_WEIGHTS; }
   cudaStreamSynchronize(e->stream);
   if (!e->evaluator.upload(net, &err)) { e->set_error("spb_load_weights: " + err); return SPB_ERR_CUDA; }
+  // The captured step graph holds the address of the previous weight image in its kernel nodes (hot swap between
+  // generations, learner_concurrent.rs:158-159): drop it, the next search captures the new one.
+  if (e->step_graph) { cudaGraphExecDestroy(e->step_graph); e->step_graph = nullptr; }
+  e->last_eval_parity = -1;
   return SPB_OK;
 }
 
@@ -1092,7 +1216,7 @@ int32_t spb_reset_games(spb_engine* e, const uint32_t* slots, uint32_t n, const 
     cudaError_t ce = cudaMemcpyAsync(e->d_stage, e->h_stage, bytes, cudaMemcpyHostToDevice, e->stream);
     if (ce != cudaSuccess) { e->set_error(cudaGetErrorString(ce)); return SPB_ERR_CUDA; }
     auto* ds = static_cast<uint8_t*>(e->d_stage);
-    k_reset<<<(n + 127) / 128, 128, 0, e->stream>>>(e->T, e->P.hist_len, slots ? reinterpret_cast<uint32_t*>(ds) : nullptr,
+    k_reset<<<(n + 127) / 128, 128, 0, e->stream>>>(e->T, e->P.hist_len, e->P.parked, slots ? reinterpret_cast<uint32_t*>(ds) : nullptr,
                                                     roots ? reinterpret_cast<PState*>(ds + off_roots) : nullptr, n);
     ++e->launches;
     ce = cudaGetLastError();
@@ -1537,16 +1661,23 @@ int32_t spb_time_evaluator(spb_engine* e, uint32_t iters, float* avg_ms, uint32_
   ENGINE_GUARD(e);
   ARG_CHECK(e, iters > 0 && avg_ms, "bad argument");
   if (e->cfg.evaluator != SPB_EVAL_NET || !e->evaluator.loaded()) { e->set_error("needs the network evaluator with weights loaded"); return SPB_ERR_STATE; }
-  if (e->last_eval_parity < 0) { e->set_error("run spb_search first"); return SPB_ERR_STATE; }
   const uint32_t slots = e->T.G * e->T.K;
   const uint32_t* cnt = &e->T.eval_count[2];
   const bool simt = (e->cfg.flags & SPB_FLAG_EVAL_SIMT) != 0;
   cudaError_t ce = cudaSuccess;
+  // Lock-step pipeline: the work list of the last simulation step.  Asynchronous pipeline (no step lists): the latest
+  // evaluated leaf of every slot, as one static list of G positions.
+  const uint32_t* list = e->T.eval_list;
+  if (e->last_eval_parity < 0) {
+    list = nullptr;
+    ce = cudaMemcpyAsync(&e->T.eval_count[2], &slots, 4, cudaMemcpyHostToDevice, e->stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+  }
   for (int w = 0; w < 2 && ce == cudaSuccess; ++w)    // warm-up
-    ce = e->evaluator.launch(e->T.leaf_state, e->T.eval_list, cnt, slots, e->T.eval_out, e->eval_stride, nullptr, simt, e->stream, /*overlap=*/false);
+    ce = e->evaluator.launch(e->T.leaf_state, list, cnt, slots, e->T.eval_out, e->eval_stride, nullptr, simt, e->stream, /*overlap=*/false);
   if (ce == cudaSuccess) ce = cudaEventRecord(e->ev0, e->stream);
   for (uint32_t i = 0; i < iters && ce == cudaSuccess; ++i)
-    ce = e->evaluator.launch(e->T.leaf_state, e->T.eval_list, cnt, slots, e->T.eval_out, e->eval_stride, nullptr, simt, e->stream, /*overlap=*/false);
+    ce = e->evaluator.launch(e->T.leaf_state, list, cnt, slots, e->T.eval_out, e->eval_stride, nullptr, simt, e->stream, /*overlap=*/false);
   if (ce == cudaSuccess) ce = cudaEventRecord(e->ev1, e->stream);
   uint32_t n = 0;
   if (ce == cudaSuccess) ce = cudaMemcpyAsync(&n, cnt, 4, cudaMemcpyDeviceToHost, e->stream);
@@ -1558,6 +1689,12 @@ int32_t spb_time_evaluator(spb_engine* e, uint32_t iters, float* avg_ms, uint32_
   *avg_ms = ms / (float)iters;
   if (n_positions) *n_positions = n;
   if (flops_per_position) *flops_per_position = e->evaluator.flops_per_position();
+  return SPB_OK;
+}
+
+int32_t spb_last_async_stats(spb_engine* e, uint64_t* out, uint32_t n) {
+  if (!e || !out) return SPB_ERR_ARG;
+  for (uint32_t i = 0; i < n; ++i) out[i] = i < (uint32_t)ASTAT_COUNT ? e->last_async_stats[i] : 0;
   return SPB_OK;
 }
 

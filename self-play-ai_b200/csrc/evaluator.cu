@@ -158,23 +158,23 @@ bool Evaluator::upload(const HostNet& net, std::string* err) {
   std::memcpy(blob.data() + off_vw, net.vfc_w.data(), net.vfc_w.size() * 4);
   std::memcpy(blob.data() + off_vb, net.vfc_b.data(), net.vfc_b.size() * 4);
   // tcgen05 operand images + epilogue tables
-  std::vector<uint8_t> umma1;
-  umma_v1::pack_weights(net, &umma1);
-  const size_t off_umma1 = reserve(umma1.size());
-  std::memcpy(blob.data() + off_umma1, umma1.data(), umma1.size());
-  std::vector<uint8_t> umma3;
-  umma_v3::pack_weights(net, &umma3);
-  const size_t off_umma3 = reserve(umma3.size());
-  std::memcpy(blob.data() + off_umma3, umma3.data(), umma3.size());
-  std::vector<uint8_t> umma2;
-  umma_v2::pack_weights(net, &umma2);
-  const size_t off_umma2 = reserve(umma2.size());
-  std::memcpy(blob.data() + off_umma2, umma2.data(), umma2.size());
+  std::vector<uint8_t> umma_img;
+  umma::pack_weights(net, &umma_img);
+  const size_t off_umma = reserve(umma_img.size());
+  std::memcpy(blob.data() + off_umma, umma_img.data(), umma_img.size());
 
-  if (d_blob_) { cudaFree(d_blob_); d_blob_ = nullptr; }
-  cudaError_t e = cudaMalloc(&d_blob_, blob.size());
-  if (e == cudaSuccess) e = cudaMemcpy(d_blob_, blob.data(), blob.size(), cudaMemcpyHostToDevice);
-  if (e != cudaSuccess) { *err = std::string("weight upload: ") + cudaGetErrorString(e); loaded_ = false; return false; }
+  // new image first, then swap: a failed upload keeps the previous checkpoint usable
+  void* nblob = nullptr;
+  cudaError_t e = cudaMalloc(&nblob, blob.size());
+  if (e == cudaSuccess) e = cudaMemcpy(nblob, blob.data(), blob.size(), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    if (nblob) cudaFree(nblob);
+    cudaGetLastError();
+    *err = std::string("weight upload: ") + cudaGetErrorString(e);
+    return false;
+  }
+  if (d_blob_) cudaFree(d_blob_);
+  d_blob_ = nblob;
   blob_bytes_ = blob.size();
   const uint8_t* d = static_cast<const uint8_t*>(d_blob_);
   for (int i = 0; i < NET_CONVS; ++i) {
@@ -185,10 +185,7 @@ bool Evaluator::upload(const HostNet& net, std::string* err) {
   dev_.pfc_b = reinterpret_cast<const float*>(d + off_pb);
   dev_.vfc_w = reinterpret_cast<const float*>(d + off_vw);
   dev_.vfc_b = reinterpret_cast<const float*>(d + off_vb);
-  dev_.w_umma = nullptr;
-  dev_.w_umma_v1 = reinterpret_cast<const uint16_t*>(d + off_umma1);
-  dev_.w_umma_v2 = reinterpret_cast<const uint16_t*>(d + off_umma2);
-  dev_.w_umma_v3 = reinterpret_cast<const uint16_t*>(d + off_umma3);
+  dev_.w_umma = reinterpret_cast<const uint16_t*>(d + off_umma);
   dev_.rows = net.rows; dev_.cols = net.cols; dev_.actions = A;
   game_ = net.game; rows_ = net.rows; cols_ = net.cols; actions_ = A;
   (void)P;
@@ -207,17 +204,12 @@ cudaError_t Evaluator::launch(const PState* states, const uint32_t* list, const 
       k_eval_simt<TicTacToe><<<grid, 256, 0, stream>>>(dev_, states, list, count_dev, max_n, out, stride, logits_out);
     return cudaGetLastError();
   }
-  DevNet net = dev_;
-  if (use_v1_) {
-    net.w_umma = dev_.w_umma_v1;
-    return umma_v1::launch(net, game_, states, list, count_dev, max_n, out, stride, logits_out, stream);
-  }
-  if (use_v3_) {
-    net.w_umma = dev_.w_umma_v3;
-    return umma_v3::launch(net, game_, states, list, count_dev, max_n, out, stride, logits_out, stream, overlap);
-  }
-  net.w_umma = dev_.w_umma_v2;
-  return umma_v2::launch(net, game_, states, list, count_dev, max_n, out, stride, logits_out, stream, overlap);
+  return umma::launch(dev_, game_, states, list, count_dev, max_n, out, stride, logits_out, stream, overlap);
+}
+
+cudaError_t Evaluator::launch_ring(const Trees& T, const AsyncCtl& C, cudaStream_t stream) {
+  if (!loaded_) return cudaErrorNotReady;
+  return umma::launch_ring(dev_, game_, T, C, stream);
 }
 
 }  // namespace spb

@@ -13,6 +13,9 @@
 
 namespace spb {
 
+struct Trees;
+struct AsyncCtl;
+
 constexpr int NET_HIDDEN = 64;     // model/connect_four.rs:18 num_hidden
 constexpr int NET_BLOCKS = 4;      // model/connect_four.rs:18 num_resnet_blocks
 constexpr int NET_POLICY_CH = 32;  // model/connect_four.rs:60
@@ -43,8 +46,6 @@ class Evaluator {
   // Uploads the folded net: bf16 conv weights in the tcgen05 shared-memory layout + f32 biases / FCs.
   bool upload(const HostNet& net, std::string* err);
   bool loaded() const { return loaded_; }
-  void use_v3(bool v) { use_v3_ = v; }   // CTA-pair kernel (evaluator_umma_v3.cu)
-  void use_v1(bool v) { use_v1_ = v; }   // true = first tcgen05 kernel (one MMA group per tap, SPB_FLAG_EVAL_V1); default = kx-pair kernel
   int game() const { return game_; }
 
   // Evaluates states[list[i]] for i < *count_dev (count read on the device; at most max_n) and writes
@@ -54,13 +55,15 @@ class Evaluator {
   cudaError_t launch(const PState* states, const uint32_t* list, const uint32_t* count_dev, uint32_t max_n,
                      float* out, int stride, float* logits_out, bool simt, cudaStream_t stream, bool overlap = true);
 
+  // Asynchronous search pipeline (async.cuh): launches the resident evaluator + tree-warp kernel that serves the leaf
+  // ring until every tree of the search is done.
+  cudaError_t launch_ring(const Trees& T, const AsyncCtl& C, cudaStream_t stream);
+
   // FLOPs per evaluated position (2*MAC over convs and FCs; SURVEY.md §8a: 26,630,268 for Connect4).
   double flops_per_position() const;
 
  private:
   bool loaded_ = false;
-  bool use_v1_ = false;
-  bool use_v3_ = false;
   int game_ = -1, rows_ = 0, cols_ = 0, actions_ = 0;
   void* d_blob_ = nullptr;      // one allocation holding everything below
   size_t blob_bytes_ = 0;
@@ -69,10 +72,7 @@ class Evaluator {
   struct DevNet {
     const uint16_t* w_simt[NET_CONVS];   // bf16 [OC][IC*9] (k = ic*9 + tap), SIMT kernel
     const float* bias[NET_CONVS];        // f32 [OC]
-    const uint16_t* w_umma;              // image the launched tcgen05 kernel reads (set per launch to one of the two below)
-    const uint16_t* w_umma_v1;           // image of the first kernel (one MMA group per tap, evaluator_umma_v1.cu)
-    const uint16_t* w_umma_v3;           // image of the CTA-pair kernel (evaluator_umma_v3.cu)
-    const uint16_t* w_umma_v2;           // image of the default kx-pair kernel (evaluator_umma_v2.cu)
+    const uint16_t* w_umma;              // weight image of the tcgen05 kernel (evaluator_umma.cu: UMMA operand layout)
     const float* pfc_w; const float* pfc_b; const float* vfc_w; const float* vfc_b;
     int rows, cols, actions;
   } dev_{};

@@ -98,13 +98,26 @@ struct WarpPath {
   float W[2];
 };
 
+// Node-record load.  COHERENT = read at L2 (ld.global.cg): required when another SM may have written the tree since this SM
+// last cached it (the asynchronous pipeline hands a tree from SM to SM); the lock-step and fused kernels keep L1.
+template <bool COHERENT>
+__device__ __forceinline__ NodeRec ld_rec(const NodeRec* p) {
+  if (COHERENT) {
+    const uint4 v = __ldcg(reinterpret_cast<const uint4*>(p));
+    NodeRec r;
+    r.N = v.x; r.W = __uint_as_float(v.y); r.P = __uint_as_float(v.z); r.info = v.w;
+    return r;
+  }
+  return *p;
+}
+
 // Descend from the root to a leaf (mcts.rs:237-241), replaying the moves on the bitboards.
 // All lanes return the same (leaf, depth, st, leaf_info).
-template <class G>
+template <class G, bool COHERENT = false>
 __device__ __forceinline__ void descend(const NodeRec* rec, const PState& root, float c, int lane,
                                         WarpPath& path, uint32_t& leaf, int& depth, PState& st, uint32_t& leaf_info,
                                         uint32_t* err) {
-  NodeRec r0 = rec[0];
+  NodeRec r0 = ld_rec<COHERENT>(rec);
   uint32_t node = 0, Np = r0.N, info = r0.info;
   st = root;
   depth = 0;
@@ -117,7 +130,7 @@ __device__ __forceinline__ void descend(const NodeRec* rec, const PState& root, 
     float score = -INFINITY;
     int idx = -1;
     if (lane < nc) {
-      ch = rec[fc + lane];                                   // 16-B vector load, children contiguous
+      ch = ld_rec<COHERENT>(rec + fc + lane);                // 16-B vector load, children contiguous
       score = puct_score(c, Np, ch.N, ch.W, ch.P);
       idx = lane;
       if (score != score) atomicOr(err, ERRBIT_NAN);         // the reference would panic (partial_cmp().unwrap())

@@ -16,9 +16,9 @@ ONGOING, TIED, WON = 0, 1, 2
 MAX_ACTIONS = 9
 NUM_ACTIONS = {GAME_TTT: 9, GAME_C4: 7}
 BOARD = {GAME_TTT: (3, 3), GAME_C4: (6, 7)}
-FLAG_NO_GRAPH, FLAG_EVAL_SIMT, FLAG_FORCE_SPLIT, FLAG_FIXED_POOL, FLAG_EVAL_V1, FLAG_EVAL_PAIR2 = 1, 2, 4, 16, 32, 64
+FLAG_NO_GRAPH, FLAG_EVAL_SIMT, FLAG_FORCE_SPLIT, FLAG_FIXED_POOL, FLAG_LOCKSTEP = 1, 2, 4, 16, 32
 MOVE_GREEDY_LAST_MAX, MOVE_TEMPERATURE = 0, 1
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class EngineError(RuntimeError):
@@ -44,7 +44,7 @@ class Config(C.Structure):
     _fields_ = [("abi_version", C.c_uint32), ("game", C.c_int32), ("device", C.c_int32), ("num_games", C.c_uint32),
                 ("max_nodes_per_tree", C.c_uint32), ("leaves_per_tree", C.c_uint32), ("c", C.c_float),
                 ("evaluator", C.c_int32), ("flags", C.c_uint32), ("game_id_base", C.c_uint32),
-                ("game_id_stride", C.c_uint32), ("reserved", C.c_uint32 * 5)]
+                ("game_id_stride", C.c_uint32), ("trajectory_capacity", C.c_uint32), ("reserved", C.c_uint32 * 4)]
 
 
 class Counters(C.Structure):
@@ -98,6 +98,7 @@ ABI = {
     "spb_reset_counters": (C.c_int32, [_vp]),
     "spb_last_search_timing": (C.c_int32, [_vp, _f32p, _f32p, _u32p]),
     "spb_synchronize": (C.c_int32, [_vp]),
+    "spb_last_async_stats": (C.c_int32, [_vp, C.POINTER(C.c_uint64), C.c_uint32]),
     "spb_time_evaluator": (C.c_int32, [_vp, C.c_uint32, _f32p, _u32p, C.POINTER(C.c_double)]),
 }
 
@@ -157,13 +158,14 @@ class Engine:
     """One engine = `Mcts` + its `Vec<Tree>` on one GPU (ref: mcts.rs:41-44, learner_concurrent.rs:174)."""
 
     def __init__(self, game=GAME_C4, num_games=100, evaluator=EVAL_NET, c=2.0, device=0, max_nodes_per_tree=0,
-                 flags=0, leaves_per_tree=1, game_id_base=0, game_id_stride=0):
+                 flags=0, leaves_per_tree=1, game_id_base=0, game_id_stride=0, trajectory_capacity=0):
         L = load_library()
         cfg = Config()
         L.spb_default_config(C.byref(cfg))
         cfg.game, cfg.num_games, cfg.evaluator, cfg.c, cfg.device = game, num_games, evaluator, c, device
         cfg.max_nodes_per_tree, cfg.flags, cfg.leaves_per_tree = max_nodes_per_tree, flags, leaves_per_tree
         cfg.game_id_base, cfg.game_id_stride = game_id_base, game_id_stride
+        cfg.trajectory_capacity = trajectory_capacity
         h = _vp()
         rc = L.spb_create(C.byref(cfg), C.byref(h))
         if rc != 0:
@@ -324,6 +326,14 @@ class Engine:
         ms, n, fl = C.c_float(), C.c_uint32(), C.c_double()
         self._chk(self._L.spb_time_evaluator(self._h, iters, C.byref(ms), C.byref(n), C.byref(fl)))
         return ms.value, n.value, fl.value
+
+    def async_stats(self) -> dict:
+        """Statistics of the last search through the asynchronous pipeline (see spb_last_async_stats)."""
+        v = (C.c_uint64 * 12)()
+        self._chk(self._L.spb_last_async_stats(self._h, v, 12))
+        names = ("batches", "boards", "claim_wait_ns", "tree_busy_ns", "tree_visits", "tree_warps", "eval_ctas",
+                 "claims_found_empty", "ticket_wait_ns", "avail_sum", "ready_backlog_sum", "ready_pops_starved")
+        return {k: int(x) for k, x in zip(names, v)}
 
     def synchronize(self):
         self._chk(self._L.spb_synchronize(self._h))

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(L, n), "missing export: " + n
     assert set(names) == set(S.engine.ABI), set(names) ^ set(S.engine.ABI)
-    assert L.spb_abi_version() == 1 == int(re.search(r"#define SPB_ABI_VERSION (\d+)", HEADER).group(1))
+    assert L.spb_abi_version() == S.engine.ABI_VERSION == int(re.search(r"#define SPB_ABI_VERSION (\d+)", HEADER).group(1))
 
 
 def test_struct_layouts_match_header():
@@ -97,7 +97,7 @@ def test_flag_and_code_constants_agree_across_header_python_and_rust():
     header = open(os.path.join(root, "include", "selfplay_b200.h")).read()
     defs = {m.group(1): int(m.group(2).rstrip("u"), 0) for m in re.finditer(r"#define\s+(SPB_[A-Z0-9_]+)\s+(-?\d+u?)\b", header)}
     py = {"SPB_FLAG_NO_GRAPH": S.FLAG_NO_GRAPH, "SPB_FLAG_EVAL_SIMT": S.FLAG_EVAL_SIMT, "SPB_FLAG_FORCE_SPLIT": S.FLAG_FORCE_SPLIT,
-          "SPB_FLAG_FIXED_POOL": S.FLAG_FIXED_POOL, "SPB_FLAG_EVAL_V1": S.FLAG_EVAL_V1, "SPB_FLAG_EVAL_PAIR2": S.FLAG_EVAL_PAIR2,
+          "SPB_FLAG_FIXED_POOL": S.FLAG_FIXED_POOL, "SPB_FLAG_LOCKSTEP": S.FLAG_LOCKSTEP,
           "SPB_GAME_CONNECT4": S.GAME_C4, "SPB_GAME_TICTACTOE": S.GAME_TTT,
           "SPB_EVAL_NET": S.EVAL_NET, "SPB_EVAL_DET": S.EVAL_DET, "SPB_EVAL_UNIFORM": S.EVAL_UNIFORM}
     for name, value in py.items():

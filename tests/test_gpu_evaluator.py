@@ -44,30 +44,6 @@ def test_tcgen05_evaluator_matches_torch(game, n):
     _check(game, 0, n, 2, torch_net.to_safetensors_tch)
 
 
-@pytest.mark.parametrize("game", [S.GAME_C4, S.GAME_TTT], ids=["c4", "ttt"])
-@pytest.mark.parametrize("n", [1, 19, 2000])
-def test_first_tcgen05_kernel_matches_torch(game, n):
-    """SPB_FLAG_EVAL_V1: one MMA group per tap (N = 64), kept as a cross-check of the default kx-pair kernel."""
-    _check(game, S.FLAG_EVAL_V1, n, 2, torch_net.to_safetensors_tch)
-
-
-@pytest.mark.parametrize("game", [S.GAME_C4, S.GAME_TTT], ids=["c4", "ttt"])
-@pytest.mark.parametrize("n", [1, 2, 19, 37, 2000])
-def test_cta_pair_kernel_is_bit_identical_to_the_default(game, n):
-    """SPB_FLAG_EVAL_PAIR2 (tcgen05 cta_group::2: two CTAs share every B operand) performs the same arithmetic in the same
-    order as the default kernel: identical logits, values and policies for every batch shape (odd counts leave the peer
-    CTA of a pair with fewer or no boards)."""
-    net = torch_net.make_net(game, seed=5)
-    states = random_states(game, n, seed=11, include_terminal=False)
-    outs = []
-    for flags in (0, S.FLAG_EVAL_PAIR2):
-        with S.Engine(game=game, num_games=4, evaluator=S.EVAL_NET, flags=flags) as e:
-            e.load_weights(torch_net.to_safetensors_tch(net))
-            outs.append(e.predict(states, want_logits=True))
-    for a, b in zip(outs[0], outs[1]):
-        assert np.array_equal(a, b)
-
-
 def test_tcgen05_and_simt_agree_closely():
     lg0, v0 = _check(S.GAME_C4, 0, 257, 4, torch_net.to_safetensors_explicit)
     lg1, v1 = _check(S.GAME_C4, S.FLAG_EVAL_SIMT, 257, 4, torch_net.to_safetensors_explicit)
@@ -75,7 +51,7 @@ def test_tcgen05_and_simt_agree_closely():
     assert np.abs(lg0 - lg1).max() <= 2e-3 * scale and np.abs(v0 - v1).max() <= 2e-3
 
 
-@pytest.mark.parametrize("flags", [0, S.FLAG_NO_GRAPH], ids=["graph", "nograph"])
+@pytest.mark.parametrize("flags", [0, S.FLAG_LOCKSTEP, S.FLAG_LOCKSTEP | S.FLAG_NO_GRAPH], ids=["async", "lockstep-graph", "lockstep-nograph"])
 def test_network_search_invariants(flags):
     G, sims = 64, 120
     net = torch_net.make_net(S.GAME_C4, seed=0)
@@ -116,3 +92,74 @@ def test_network_search_close_to_oracle_with_torch_evaluator():
         for slot in range(G):
             tv += np.abs(e.root_policy(slot) - f.root_policy(slot)).sum() / 2
     assert tv / G < 0.05, tv / G
+
+
+@pytest.mark.parametrize("game,G,sims", [(S.GAME_C4, 300, 150), (S.GAME_C4, 5, 64), (S.GAME_TTT, 200, 90)], ids=["c4-300", "c4-5", "ttt-200"])
+def test_async_pipeline_equals_lockstep_pipeline_with_the_network(game, G, sims):
+    """The asynchronous pipeline (default) drops the reference's lock-step across trees (mcts.rs:214) but not its
+    results: the evaluator is a pure function of one position and a tree's simulations stay sequential, so every node
+    statistic equals the literal lock-step pipeline's, bit for bit — also across accumulating searches and re-rooting."""
+    net = torch_net.make_net(game, seed=3)
+    blob = torch_net.to_safetensors_tch(net)
+    roots = synthetic_roots(game, G, start=7, max_ply=21 if game == S.GAME_C4 else 4)
+    snaps = []
+    for flags in (0, S.FLAG_LOCKSTEP):
+        with S.Engine(game=game, num_games=G, evaluator=S.EVAL_NET, flags=flags) as e:
+            e.load_weights(blob)
+            e.reset_games(roots)
+            e.reset_counters()
+            snap = []
+            e.search(sims)
+            snap.append([x.copy() for x in e.root_children_all()])
+            e.search(7)                                           # accumulates on top (mcts.rs:214 on a searched tree)
+            a, c, i, n = e.root_children_all()
+            snap.append([a.copy(), c.copy(), i.copy(), n.copy()])
+            live = [g for g in range(G) if n[g] > 0]
+            best = [int(i[g][max(range(n[g]), key=lambda j: (c[g][j], j))]) for g in live]
+            e.advance(best, slots=live)                           # use_subtree (mcts.rs:161-192)
+            e.search(31)
+            snap.append([x.copy() for x in e.root_children_all()])
+            snap.append([e.node_stats(g, k) for g in live[:6] for k in range(min(e.arena_len(g), 40))])
+            snap.append(e.counters())
+        snaps.append(snap)
+    for x, y in zip(snaps[0][:3], snaps[1][:3]):
+        for u, v in zip(x, y):
+            assert np.array_equal(u, v)
+    assert snaps[0][3] == snaps[1][3]
+    for k in ("simulations", "evaluations", "terminal_leaves", "path_length_sum", "children_created", "nodes_live"):
+        assert snaps[0][4][k] == snaps[1][4][k], k
+
+
+def test_weight_hot_swap_between_searches():
+    """learner_concurrent.rs:158-159 publishes new weights between generations: a second spb_load_weights on an engine
+    that has already searched must be what the following predict / search use — on every pipeline (the lock-step
+    pipeline replays a captured CUDA graph that held the old weight image's address)."""
+    G, sims = 48, 40
+    roots = synthetic_roots(S.GAME_C4, G, start=3)
+    blob_a = torch_net.to_safetensors_tch(torch_net.make_net(S.GAME_C4, seed=11))
+    blob_b = torch_net.to_safetensors_tch(torch_net.make_net(S.GAME_C4, seed=12))
+    for flags in (0, S.FLAG_LOCKSTEP, S.FLAG_LOCKSTEP | S.FLAG_NO_GRAPH):
+        with S.Engine(game=S.GAME_C4, num_games=G, evaluator=S.EVAL_NET, flags=flags) as fresh:
+            fresh.load_weights(blob_b)
+            want_pred = fresh.predict(roots[:16], want_logits=True)
+            fresh.reset_games(roots)
+            fresh.search(sims)
+            want = fresh.root_children_all()
+        with S.Engine(game=S.GAME_C4, num_games=G, evaluator=S.EVAL_NET, flags=flags) as e:
+            e.load_weights(blob_a)
+            e.reset_games(roots)
+            e.search(sims)                                        # captures the graph with checkpoint A
+            first = e.root_children_all()
+            e.load_weights(blob_b)
+            for _ in range(3):                                    # freed-and-reallocated images move around
+                e.load_weights(blob_a)
+                e.load_weights(blob_b)
+            got_pred = e.predict(roots[:16], want_logits=True)
+            e.reset_games(roots)
+            e.search(sims)
+            got = e.root_children_all()
+        for u, v in zip(want_pred, got_pred):
+            assert np.array_equal(u, v)
+        for u, v in zip(want, got):
+            assert np.array_equal(u, v)
+        assert not np.array_equal(first[1], got[1])               # the two checkpoints do search differently

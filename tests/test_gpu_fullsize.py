@@ -43,7 +43,7 @@ def test_full_size_deterministic_evaluator_sampled_oracle_and_pipeline_agreement
     sample = list(range(0, G, 171))                       # 24 trees spread over the batch
     f = O.Forest(O.GAME_C4, len(sample))
     digests = []
-    for flags in (0, S.FLAG_FORCE_SPLIT):
+    for flags in (0, S.FLAG_FORCE_SPLIT, S.FLAG_FORCE_SPLIT | S.FLAG_LOCKSTEP):       # fused, asynchronous, lock-step
         with S.Engine(game=S.GAME_C4, num_games=G, evaluator=S.EVAL_DET, flags=flags) as e:
             roots = synthetic_roots_device(e, G)
             e.reset_games(roots)
@@ -64,16 +64,16 @@ def test_full_size_deterministic_evaluator_sampled_oracle_and_pipeline_agreement
                 assert e.node_stats(g, 0) == f.node_stats(k, 0)
                 last = f.arena_len(k) - 1
                 assert e.node_stats(g, last) == f.node_stats(k, last)
-    assert digests[0] == digests[1]                        # all 4,096 trees: fused == lock-step, bit for bit
+    assert digests[0] == digests[1] == digests[2]          # all 4,096 trees: fused == asynchronous == lock-step, bit for bit
 
 
 def test_full_size_network_search_is_conserving_and_reproducible():
     """The tcgen05 evaluator reduces in a fixed order per board, so the result of a search does not depend on how
-    leaves were batched: two searches from the same roots, the CUDA-graph and direct-launch pipelines and the CTA-pair
-    evaluator give identical visit counts for all 4,096 trees."""
+    leaves were batched: two searches from the same roots through the asynchronous pipeline, the lock-step CUDA-graph
+    pipeline and the lock-step direct-launch pipeline give identical visit counts for all 4,096 trees."""
     blob = random_checkpoint(1, 0)
     seen = []
-    for flags in (0, S.FLAG_NO_GRAPH, S.FLAG_EVAL_PAIR2):          # the CTA-pair kernel computes in the same order: same trees
+    for flags in (0, S.FLAG_LOCKSTEP, S.FLAG_LOCKSTEP | S.FLAG_NO_GRAPH):
         with S.Engine(game=S.GAME_C4, num_games=G, evaluator=S.EVAL_NET, flags=flags) as e:
             e.load_weights(blob)
             roots = synthetic_roots_device(e, G)
@@ -161,7 +161,7 @@ def test_full_size_tictactoe_sampled_oracle_and_pipeline_agreement():
     sample = list(range(3, G, 293))
     f = O.Forest(O.GAME_TTT, len(sample))
     digests = []
-    for flags in (0, S.FLAG_FORCE_SPLIT):
+    for flags in (0, S.FLAG_FORCE_SPLIT, S.FLAG_FORCE_SPLIT | S.FLAG_LOCKSTEP):
         with S.Engine(game=S.GAME_TTT, num_games=G, evaluator=S.EVAL_DET, flags=flags) as e:
             roots = synthetic_roots_device(e, G, max_ply=5)
             e.reset_games(roots)
@@ -179,7 +179,7 @@ def test_full_size_tictactoe_sampled_oracle_and_pipeline_agreement():
                 assert e.root_children(g) == f.root_children(k), g
                 assert e.arena_len(g) == f.arena_len(k)
                 assert e.node_stats(g, 0) == f.node_stats(k, 0)
-    assert digests[0] == digests[1]
+    assert digests[0] == digests[1] == digests[2]
 
 
 def test_full_size_network_with_16_leaves_in_flight_conserves_the_budget():

@@ -23,7 +23,11 @@ def _assert_same_tree(e, f, slot, full=True):
         assert e.node_stats(slot, i) == f.node_stats(slot, i), (slot, i)
 
 
-@pytest.mark.parametrize("flags", [0, S.FLAG_FORCE_SPLIT, S.FLAG_FORCE_SPLIT | S.FLAG_NO_GRAPH], ids=["fused", "split-graph", "split"])
+PIPELINES = {"fused": 0, "async": S.FLAG_FORCE_SPLIT, "lockstep-graph": S.FLAG_FORCE_SPLIT | S.FLAG_LOCKSTEP,
+             "lockstep": S.FLAG_FORCE_SPLIT | S.FLAG_LOCKSTEP | S.FLAG_NO_GRAPH}
+
+
+@pytest.mark.parametrize("flags", list(PIPELINES.values()), ids=list(PIPELINES))
 def test_survey_kats_on_device(flags):
     for S_, ev, key in [(800, S.EVAL_DET, "c4_det"), (100, S.EVAL_DET, "c4_det"), (800, S.EVAL_UNIFORM, "c4_uniform"), (9, S.EVAL_UNIFORM, "c4_uniform")]:
         with S.Engine(game=S.GAME_C4, num_games=3, evaluator=ev, flags=flags) as e:
@@ -46,7 +50,7 @@ def test_survey_kats_on_device(flags):
 
 
 @pytest.mark.parametrize("game,ev", [(S.GAME_C4, S.EVAL_DET), (S.GAME_C4, S.EVAL_UNIFORM), (S.GAME_TTT, S.EVAL_DET)])
-@pytest.mark.parametrize("flags", [0, S.FLAG_FORCE_SPLIT], ids=["fused", "split"])
+@pytest.mark.parametrize("flags", list(PIPELINES.values())[:3], ids=list(PIPELINES)[:3])
 def test_search_matches_oracle_node_for_node(game, ev, flags):
     G = 48
     roots = synthetic_roots(game, G, start=100, max_ply=21 if game == S.GAME_C4 else 5)
@@ -187,7 +191,7 @@ def test_fixed_pool_exhaustion_is_an_error_not_ub():
         assert sum(e.root_children(0)[1]) == 4
 
 
-@pytest.mark.parametrize("flags", [0, S.FLAG_FORCE_SPLIT], ids=["fused", "split-graph"])
+@pytest.mark.parametrize("flags", list(PIPELINES.values())[:3], ids=list(PIPELINES)[:3])
 def test_pools_grow_like_the_reference_arena(flags):
     """mcts.rs:19 — the reference's arena is an unbounded Vec.  Starting from 16 nodes per tree, the pools are widened
     before each search that could outgrow them and the trees stay bit-identical to the oracle, re-roots included."""
@@ -274,3 +278,35 @@ def test_one_process_can_drive_engines_on_several_gpus():
             res.append([e.root_children(s) for s in range(40)])
     assert res[0] == res[1]
     assert sum(res[0][0][1]) == 59
+
+
+def test_trajectory_buffer_overflow_parks_games_and_loses_nothing():
+    """A finished game whose trajectory does not fit the output buffer is parked, the call reports SPB_ERR_STATE, and
+    after a drain the next ply emits it: every record that is drained is complete, no game is lost, and the union of all
+    drains equals the trajectories of an engine with a large buffer."""
+    G, sims = 64, 30
+
+    def play(capacity):
+        out = []
+        with S.Engine(game=S.GAME_TTT, num_games=G, evaluator=S.EVAL_DET, trajectory_capacity=capacity) as e:
+            e.reset_games()
+            errors = 0
+            for _ in range(40):
+                e.search(sims)
+                try:
+                    e.selfplay_step(S.MOVE_GREEDY_LAST_MAX)
+                except S.EngineError as err:
+                    assert err.code == -6 and "trajectory buffer full" in str(err)
+                    errors += 1
+                pos, ids = e.drain_trajectories()
+                assert len(pos) <= max(capacity, 9) or capacity == 0
+                out += [(int(i), p.tobytes()) for p, i in zip(pos, ids)]
+            e.selfplay_step(S.MOVE_GREEDY_LAST_MAX)               # emits what is still parked
+            pos, ids = e.drain_trajectories()
+            out += [(int(i), p.tobytes()) for p, i in zip(pos, ids)]
+        return sorted(out), errors
+
+    want, e0 = play(0)
+    got, e1 = play(20)                                            # room for two or three games per ply
+    assert e0 == 0 and e1 > 0
+    assert len(want) > G * 5 and got == want
