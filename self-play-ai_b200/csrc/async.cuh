@@ -50,6 +50,15 @@ __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long
 __device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned long long v) {
   asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+// Polling uses relaxed loads (served by L2, no side effects on the SM); the acquire is a fence executed once, after the
+// awaited value has been seen.  An acquire load in the polling loop costs an L1 invalidation per poll, which slowed the
+// evaluator sharing the SM by ~10 % (profiles/r02_async_trace.txt).
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void fence_acquire_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 __device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p) {
   uint32_t v;
   asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -83,10 +92,17 @@ struct Spin {
   // one unsuccessful poll; returns true when the caller must give up
   __device__ __forceinline__ bool idle(const AsyncCtl& c) {
     ++iter;
+    // Every poll is a global load through the SM's L1TEX data pipe, which the evaluator's shared-memory traffic saturates:
+    // idle warps poll rarely (measured: 87 polls per microsecond per SM with short sleeps cost 7 % of the pipe).
+#ifdef SPB_POLL_FAST
     __nanosleep((iter < 8u) ? 32u : 200u);
     if ((iter & 15u) != 0u) return false;
+#else
+    __nanosleep((iter < 4u) ? 100u : 1000u);
+    if ((iter & 7u) != 0u) return false;
+#endif
     if (over(c)) return true;
-    if ((iter & 1023u) == 0u) {
+    if ((iter & 255u) == 0u) {
       const uint32_t p = ld_relaxed_u32(c.leaf.tail) + ld_relaxed_u32(c.ready.tail);
       const unsigned long long now = gtime_ns();
       if (p != seen) { seen = p; t_last = now; }
@@ -120,8 +136,8 @@ __device__ __forceinline__ uint32_t ready_pop_wait(const AsyncCtl& c, Spin& sp) 
     if (backlog > 0) { sp.backlog += (unsigned)backlog; } else { sp.starved += 1; }
   }
   for (;;) {
-    const unsigned long long v = ld_acquire_u64(p);
-    if ((uint32_t)(v >> 32) == t + 1u) return (uint32_t)v;
+    const unsigned long long v = ld_relaxed_u64(p);
+    if ((uint32_t)(v >> 32) == t + 1u) { fence_acquire_gpu(); return (uint32_t)v; }
     if (sp.idle(c)) return RING_NONE;
   }
 }
@@ -154,7 +170,7 @@ __device__ __forceinline__ uint32_t claim_batch(const AsyncCtl& c, LeafClaimer& 
     const unsigned long long* p = &c.leaf.slots[lc.tk & c.leaf.mask];
     sp.progressed();
     for (;;) {
-      const unsigned long long v = ld_acquire_u64(p);
+      const unsigned long long v = ld_relaxed_u64(p);
       if ((uint32_t)(v >> 32) == lc.tk + 1u) { val = (uint32_t)v; break; }
       if (sp.idle(c)) break;
     }
@@ -164,11 +180,12 @@ __device__ __forceinline__ uint32_t claim_batch(const AsyncCtl& c, LeafClaimer& 
     const unsigned long long* p = &c.leaf.slots[lc.tk & c.leaf.mask];
     const unsigned long long t0 = gtime_ns();
     for (;;) {
-      const unsigned long long v = ld_acquire_u64(p);
+      const unsigned long long v = ld_relaxed_u64(p);
       if ((uint32_t)(v >> 32) == lc.tk + 1u) { val = (uint32_t)v; break; }
       if (gtime_ns() - t0 > grace_ns) break;
     }
   }
+  fence_acquire_gpu();                                              // the leaves' states are read after this (every lane reads its own)
   const uint32_t filled = __ballot_sync(0xffffffffu, (uint32_t)lane < lc.n_tk && val != RING_NONE);
   const uint32_t nb = (filled == 0xffffffffu) ? 32u : (uint32_t)__ffs((int)~filled) - 1u;   // leading filled tickets (at least the first)
   *slot_out = val;

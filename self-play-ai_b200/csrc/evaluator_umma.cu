@@ -356,7 +356,10 @@ static_assert(Geo<Connect4>::NB <= 32 && Geo<TicTacToe>::NB <= 32, "one stager l
 static_assert(Smem<Connect4>::TOTAL <= 232448 && Smem<TicTacToe>::TOTAL <= 232448, "shared memory plan exceeds 227 KB");
 constexpr int THREADS = 352;     // producer warp, MMA warp, 8 epilogue warps, stager warp
 constexpr int STAGER_WARP = 10;
-constexpr int TREE_WARPS = 5;    // asynchronous pipeline: tree warps that share the CTA (and the SM's idle issue slots)
+#ifndef SPB_TREE_WARPS
+#define SPB_TREE_WARPS 5
+#endif
+constexpr int TREE_WARPS = SPB_TREE_WARPS;    // asynchronous pipeline: tree warps that share the CTA (and the SM's idle issue slots)
 constexpr int THREADS_RING = THREADS + 32 * TREE_WARPS;
 constexpr uint32_t CLAIM_GRACE_NS = 4000;   // a batch waits this long for tickets behind its first filled one
 
@@ -375,18 +378,26 @@ struct EvalWork {
 // trace build only (make VARIANT=-DSPB_TRACE): time stamps of CTA 0, plain stores (no read-modify-write), so the
 // timeline is that of the production kernel
 __device__ unsigned long long g_trace[4][512];   // [0] MMA issue begin, [1] MMA issue end, [2] epilogue body begin, [3] body end; index (b*10+l)*4+t
-#define TRACE(k, b, l, t) do { if (blockIdx.x == 0 && (b) < 12) g_trace[k][(((b) * 10 + (l)) * 4 + (t))] = clock64(); } while (0)
+#define TRACE_B0 (RING ? 300u : 0u)   // asynchronous pipeline: a window of batches in the steady state
+#define TRACE(k, b, l, t) do { if (blockIdx.x == 0 && (b) >= TRACE_B0 && (b) < TRACE_B0 + 12u) g_trace[k][((((b) - TRACE_B0) * 10 + (l)) * 4 + (t))] = clock64(); } while (0)
+__device__ unsigned long long g_trace_stager[16][4];   // per traced batch: claim begin, claim end, act0_free seen, staged
 __device__ unsigned long long g_eval_times[64][4];   // globaltimer: [launch][entry, after griddepcontrol.wait, exit] of CTA 0
 __device__ unsigned int g_eval_idx = 0;
 __device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
-#define TRACE2(i) do { if (blockIdx.x == 0 && bb == 0 && lane == 0) g_trace[3][480 + (warp == 2 ? 0 : 8) + (i)] = clock64(); } while (0)
+#define TRACE_ST(b, i) do { if (blockIdx.x == 0 && lane == 0 && (b) >= TRACE_B0 && (b) < TRACE_B0 + 12u) g_trace_stager[(b) - TRACE_B0][i] = clock64(); } while (0)
+#define TRACE2(i) do { if (blockIdx.x == 0 && bb == TRACE_B0 && lane == 0) g_trace[3][480 + (warp == 2 ? 0 : 8) + (i)] = clock64(); } while (0)
 #else
 #define TRACE2(i) ((void)0)
 #define TRACE(k, b, l, t) ((void)0)
+#define TRACE_ST(b, i) ((void)0)
 #endif
 
 template <class G, bool RING>
+#ifdef SPB_NONRING_512
+__global__ void __launch_bounds__(512, 1)
+#else
 __global__ void __launch_bounds__(RING ? THREADS_RING : THREADS, 1)
+#endif
 k_eval_umma(const uint8_t* __restrict__ image, const EvalWork W, const Trees T, const AsyncCtl C) {
   using Ge = Geo<G>;
   using Sm = Smem<G>;
@@ -564,6 +575,11 @@ k_eval_umma(const uint8_t* __restrict__ image, const EvalWork W, const Trees T, 
     if (RING) sp.init(C, *C.n_active);
     unsigned long long st_batches = 0, st_boards = 0, st_wait = 0;
     LeafClaimer lc;
+#ifdef SPB_SPLIT_CTAS
+    const uint32_t N_EVAL_CTAS = ncta - SPB_SPLIT_CTAS;
+#else
+    const uint32_t N_EVAL_CTAS = ncta;
+#endif
     for (uint32_t bb = 0;; ++bb) {
       uint32_t nb = 0;
       PState st_mine = PState{};
@@ -572,8 +588,13 @@ k_eval_umma(const uint8_t* __restrict__ image, const EvalWork W, const Trees T, 
         // asynchronous pipeline: claim the batch from the leaf ring once the previous batch has reached layer 7
         if (bb > 0) mbar_wait_backoff<64>(bar_claim_go, (bb - 1) & 1u);
         const unsigned long long tw0 = gtime_ns();
-        nb = claim_batch(C, lc, ncta, (uint32_t)Ge::NB, CLAIM_GRACE_NS, sp, lane, &slot_mine);
+        TRACE_ST(bb, 0);
+#ifdef SPB_SPLIT_CTAS
+        if (blockIdx.x + SPB_SPLIT_CTAS >= gridDim.x) nb = 0; else
+#endif
+        nb = claim_batch(C, lc, N_EVAL_CTAS, (uint32_t)Ge::NB, CLAIM_GRACE_NS, sp, lane, &slot_mine);
         if (nb) { st_wait += gtime_ns() - tw0; ++st_batches; st_boards += nb; }
+        TRACE_ST(bb, 1);
       } else {
         const uint32_t b0 = my_begin + bb * Ge::NB;
         nb = b0 < my_end ? min((uint32_t)Ge::NB, my_end - b0) : 0u;
@@ -598,6 +619,7 @@ k_eval_umma(const uint8_t* __restrict__ image, const EvalWork W, const Trees T, 
         st_mine.x = raw.x; st_mine.o = raw.y;
       }
       if (bb > 0) mbar_wait_backoff<64>(bar_act0_free, (bb - 1) & 1u);
+      TRACE_ST(bb, 2);
       PState* st_buf = s_states + (bb & 1u) * Ge::NB;
       if ((uint32_t)lane < nb) { s_slots[(bb & 1u) * Ge::NB + lane] = slot_mine; st_buf[lane] = st_mine; }
       __syncwarp();
@@ -619,6 +641,7 @@ k_eval_umma(const uint8_t* __restrict__ image, const EvalWork W, const Trees T, 
         fence_async_smem();
         mbar_arrive(bar_stage_ready(t));
       }
+      TRACE_ST(bb, 3);
     }
   } else if (warp < STAGER_WARP) {
     // ===== epilogue warps (8 warps, 256 threads): per-layer epilogues, heads =============================
@@ -644,7 +667,9 @@ k_eval_umma(const uint8_t* __restrict__ image, const EvalWork W, const Trees T, 
       const bool has_skip = (l >= 2 && (l & 1) == 0);              // second conv of a residual block
       const uint32_t cur_par = acc_par[bb & 1u];
       acc_par[bb & 1u] ^= (1u << nt) - 1u;
-      const float* bias_l = s_bias + l * 64 + half * 32;            // this thread's 32 output channels (broadcast reads)
+      // this thread's 32 output channels, broadcast reads (registers are capped at 128 in the asynchronous kernel; a by-value
+      // kernel-parameter table read through the constant cache with a dynamic index measured 3.5 % slower)
+      const float* bias_l = s_bias + l * 64 + half * 32;
       for (int t = 0; t < nt; ++t) {
         const int m = t * 128 + row_in_tile;
         const int bi = m / Ge::BS, rem = m % Ge::BS, r = rem / Ge::W8, c = rem % Ge::W8;
@@ -911,7 +936,14 @@ k_eval_umma(const uint8_t* __restrict__ image, const EvalWork W, const Trees T, 
     }
   }
 
+#if defined(SPB_SPLIT_CTAS)
+  // experiment: the last SPB_SPLIT_CTAS CTAs are tree-only (all 16 warps), the others evaluator-only
+  if (RING && blockIdx.x + SPB_SPLIT_CTAS >= gridDim.x) tree_worker<G>(T, C, lane);
+#elif defined(SPB_SKIP_SCHED1)
+  if (RING && warp > STAGER_WARP && (warp & 3) != 1) tree_worker<G>(T, C, lane);   // experiment: no tree warp on the MMA warp's scheduler
+#else
   if (RING && warp > STAGER_WARP) tree_worker<G>(T, C, lane);       // warps 11+: the tree side of the pipeline (async.cuh)
+#endif
 
   // ---- teardown -----------------------------------------------------------------------------------
   tc_fence_before();
@@ -986,6 +1018,7 @@ extern "C" int spb_debug_eval_times_v2(unsigned long long* out) {
   rc |= (int)cudaMemcpyToSymbol(g_eval_idx, &z, sizeof z);
   return rc;
 }
+extern "C" int spb_debug_trace_stager(unsigned long long* out) { return (int)cudaMemcpyFromSymbol(out, g_trace_stager, sizeof(unsigned long long) * 16 * 4); }
 extern "C" int spb_debug_trace_v2(unsigned long long* out, int reset) {
   int rc = (int)cudaMemcpyFromSymbol(out, g_trace, sizeof(unsigned long long) * 4 * 512);
   if (reset) { static unsigned long long z[4 * 512]; rc |= (int)cudaMemcpyToSymbol(g_trace, z, sizeof z); }

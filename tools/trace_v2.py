@@ -10,8 +10,8 @@ import selfplay_b200 as S
 from selfplay_b200.synth import synthetic_roots_device
 from selfplay_b200.weights_init import random_checkpoint
 G = 4096
-VER = os.environ.get("SPB_VER", "v2")
-with S.Engine(game=S.GAME_C4, num_games=G, evaluator=S.EVAL_NET, flags=S.FLAG_NO_GRAPH | (S.FLAG_EVAL_PAIR2 if VER == "v3" else 0)) as e:
+VER = "v2"
+with S.Engine(game=S.GAME_C4, num_games=G, evaluator=S.EVAL_NET, flags=S.FLAG_NO_GRAPH | S.FLAG_LOCKSTEP) as e:
     e.load_weights(random_checkpoint(1, 0))
     roots = synthetic_roots_device(e, G)
     e.reset_games(roots)
