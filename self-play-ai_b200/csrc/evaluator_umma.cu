@@ -170,8 +170,13 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm vo
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   do {
+#ifdef SPB_MBAR_HINT
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(bar), "r"(parity), "r"((uint32_t)SPB_MBAR_HINT) : "memory");
+#else
     asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
                  : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+#endif
   } while (!ok);
 }
 __device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {   // for the producer: don't hog issue slots
@@ -354,13 +359,16 @@ struct Smem {
 static_assert(Geo<Connect4>::NB <= 32 && Geo<TicTacToe>::NB <= 32, "one stager lane / one publishing lane per board");
 
 static_assert(Smem<Connect4>::TOTAL <= 232448 && Smem<TicTacToe>::TOTAL <= 232448, "shared memory plan exceeds 227 KB");
-constexpr int THREADS = 352;     // producer warp, MMA warp, 8 epilogue warps, stager warp
-constexpr int STAGER_WARP = 10;
-#ifndef SPB_TREE_WARPS
-#define SPB_TREE_WARPS 5
-#endif
-constexpr int TREE_WARPS = SPB_TREE_WARPS;    // asynchronous pipeline: tree warps that share the CTA (and the SM's idle issue slots)
-constexpr int THREADS_RING = THREADS + 32 * TREE_WARPS;
+// Warp roles.  The eight epilogue warps are warps 4..11 = warpgroups 1 and 2, so that the asynchronous kernel can move
+// registers to them with setmaxnreg (a warpgroup-wide instruction); a warp's TMEM lane quadrant is warp % 4.
+constexpr int PRODUCER_WARP = 0, MMA_WARP = 1, STAGER_WARP = 2, SPARE_WARP = 3;   // warp 3 only completes warpgroup 0
+constexpr int EPI_WARP0 = 4, N_EPI_WARPS = 8;
+constexpr int THREADS = 32 * (EPI_WARP0 + N_EPI_WARPS);   // 384: static work list (spb_predict, lock-step pipeline)
+constexpr int TREE_WARPS = 4;    // asynchronous pipeline: warps 12..15 (warpgroup 3),: tree warps that share the CTA (and the SM's idle issue slots)
+constexpr int THREADS_RING = THREADS + 32 * TREE_WARPS;   // 512 = 4 warpgroups x 128 registers = the whole register file
+// setmaxnreg budget of the asynchronous kernel: warpgroup 0 (producer, MMA issuer, stager, one idle warp) and warpgroup 3
+// (tree warps) give registers to warpgroups 1 and 2 (epilogue): 128 x 72 + 128 x 96 + 256 x 168 = 64,512 <= 65,536.
+constexpr int REGS_LIGHT = 72, REGS_TREE = 96, REGS_EPILOGUE = 168;
 constexpr uint32_t CLAIM_GRACE_NS = 4000;   // a batch waits this long for tickets behind its first filled one
 
 // Static work source (spb_predict, lock-step pipeline).  The asynchronous pipeline reads T.leaf_state / writes T.eval_out.
@@ -385,7 +393,7 @@ __device__ unsigned long long g_eval_times[64][4];   // globaltimer: [launch][en
 __device__ unsigned int g_eval_idx = 0;
 __device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 #define TRACE_ST(b, i) do { if (blockIdx.x == 0 && lane == 0 && (b) >= TRACE_B0 && (b) < TRACE_B0 + 12u) g_trace_stager[(b) - TRACE_B0][i] = clock64(); } while (0)
-#define TRACE2(i) do { if (blockIdx.x == 0 && bb == TRACE_B0 && lane == 0) g_trace[3][480 + (warp == 2 ? 0 : 8) + (i)] = clock64(); } while (0)
+#define TRACE2(i) do { if (blockIdx.x == 0 && bb == TRACE_B0 && lane == 0) g_trace[3][480 + (warp == EPI_WARP0 ? 0 : 8) + (i)] = clock64(); } while (0)
 #else
 #define TRACE2(i) ((void)0)
 #define TRACE(k, b, l, t) ((void)0)
@@ -393,11 +401,7 @@ __device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; a
 #endif
 
 template <class G, bool RING>
-#ifdef SPB_NONRING_512
-__global__ void __launch_bounds__(512, 1)
-#else
 __global__ void __launch_bounds__(RING ? THREADS_RING : THREADS, 1)
-#endif
 k_eval_umma(const uint8_t* __restrict__ image, const EvalWork W, const Trees T, const AsyncCtl C) {
   using Ge = Geo<G>;
   using Sm = Smem<G>;
@@ -458,7 +462,7 @@ k_eval_umma(const uint8_t* __restrict__ image, const EvalWork W, const Trees T, 
     mbar_init(bar_batch(0), 1); mbar_init(bar_batch(1), 1); mbar_init(bar_claim_go, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
+  if (warp == MMA_WARP) tmem_alloc(smem_u32(tmem_slot), 512);
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -479,8 +483,16 @@ k_eval_umma(const uint8_t* __restrict__ image, const EvalWork W, const Trees T, 
     return s_nb[bb & 3u];
   };
 
-  if (warp == 0) {
+  // Asynchronous kernel: register reallocation by whole warpgroups (setmaxnreg), first thing in every role's branch so
+  // that the role's code is compiled for its own budget: the epilogue warps hold two accumulator halves, the skip
+  // connection and the layer's biases in registers; the other roles are light.
+#define SPB_REGS_LIGHT() do { if (RING) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_LIGHT)); } while (0)
+#define SPB_REGS_TREE() do { if (RING) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_TREE)); } while (0)
+#define SPB_REGS_EPILOGUE() do { if (RING) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_EPILOGUE)); } while (0)
+
+  if (warp == PRODUCER_WARP) {
     // ===== weight producer: streams (layer, tap) blocks into the 9-slot ring ==========================
+    SPB_REGS_LIGHT();
     if (lane == 0) {
       uint32_t use = 0;                                           // completed fills of every slot
       for (uint32_t b = 0; wait_batch(b) != 0u; ++b) {
@@ -501,8 +513,9 @@ k_eval_umma(const uint8_t* __restrict__ image, const EvalWork W, const Trees T, 
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == MMA_WARP) {
     // ===== MMA issuer ===============================================================================
+    SPB_REGS_LIGHT();
     // The whole warp runs the (warp-uniform) control flow so that descriptors stay in uniform registers;
     // one fixed lane issues the tcgen05 instructions.
     {
@@ -569,17 +582,13 @@ k_eval_umma(const uint8_t* __restrict__ image, const EvalWork W, const Trees T, 
     // channels 0,1,2 of chunk 0; chunk 1 = 0) into activation buffer 0, then releases the stem MMAs.  It runs one
     // batch ahead of the epilogue warps: the global loads are issued before it waits for buffer 0 to be free, and the
     // stem of batch bb can start while the epilogue warps are still busy with the heads of batch bb-1.
+    SPB_REGS_LIGHT();
     PState* s_states = reinterpret_cast<PState*>(smem + Sm::OFF_STATES);
     uint32_t* s_slots = reinterpret_cast<uint32_t*>(smem + Sm::OFF_SLOTS);
     Spin sp;
     if (RING) sp.init(C, *C.n_active);
     unsigned long long st_batches = 0, st_boards = 0, st_wait = 0;
     LeafClaimer lc;
-#ifdef SPB_SPLIT_CTAS
-    const uint32_t N_EVAL_CTAS = ncta - SPB_SPLIT_CTAS;
-#else
-    const uint32_t N_EVAL_CTAS = ncta;
-#endif
     for (uint32_t bb = 0;; ++bb) {
       uint32_t nb = 0;
       PState st_mine = PState{};
@@ -589,10 +598,7 @@ k_eval_umma(const uint8_t* __restrict__ image, const EvalWork W, const Trees T, 
         if (bb > 0) mbar_wait_backoff<64>(bar_claim_go, (bb - 1) & 1u);
         const unsigned long long tw0 = gtime_ns();
         TRACE_ST(bb, 0);
-#ifdef SPB_SPLIT_CTAS
-        if (blockIdx.x + SPB_SPLIT_CTAS >= gridDim.x) nb = 0; else
-#endif
-        nb = claim_batch(C, lc, N_EVAL_CTAS, (uint32_t)Ge::NB, CLAIM_GRACE_NS, sp, lane, &slot_mine);
+        nb = claim_batch(C, lc, ncta, (uint32_t)Ge::NB, CLAIM_GRACE_NS, sp, lane, &slot_mine);
         if (nb) { st_wait += gtime_ns() - tw0; ++st_batches; st_boards += nb; }
         TRACE_ST(bb, 1);
       } else {
@@ -643,12 +649,13 @@ k_eval_umma(const uint8_t* __restrict__ image, const EvalWork W, const Trees T, 
       }
       TRACE_ST(bb, 3);
     }
-  } else if (warp < STAGER_WARP) {
+  } else if (warp >= EPI_WARP0 && warp < EPI_WARP0 + N_EPI_WARPS) {
     // ===== epilogue warps (8 warps, 256 threads): per-layer epilogues, heads =============================
     // Two warps share a TMEM lane quadrant (a tile row) and split the 64 output channels in halves.
-    const int et = tid - 64;                                       // 0..255
+    SPB_REGS_EPILOGUE();
+    const int et = tid - 32 * EPI_WARP0;                           // 0..255
     const int quad = warp & 3;                                     // TMEM lanes [32*quad, 32*quad+32)
-    const int half = (warp - 2) >> 2;                              // channels [32*half, 32*half+32)
+    const int half = (warp - EPI_WARP0) >> 2;                      // channels [32*half, 32*half+32)
     const int row_in_tile = quad * 32 + lane;
     const float* s_bias = reinterpret_cast<const float*>(smem + Sm::OFF_BIAS);
     float* s_logits = reinterpret_cast<float*>(smem + Sm::OFF_LOGITS);
@@ -667,9 +674,12 @@ k_eval_umma(const uint8_t* __restrict__ image, const EvalWork W, const Trees T, 
       const bool has_skip = (l >= 2 && (l & 1) == 0);              // second conv of a residual block
       const uint32_t cur_par = acc_par[bb & 1u];
       acc_par[bb & 1u] ^= (1u << nt) - 1u;
-      // this thread's 32 output channels, broadcast reads (registers are capped at 128 in the asynchronous kernel; a by-value
-      // kernel-parameter table read through the constant cache with a dynamic index measured 3.5 % slower)
-      const float* bias_l = s_bias + l * 64 + half * 32;
+      float bias_r[32];                                             // this thread's 32 output channels, once per layer: a broadcast
+#pragma unroll                                                      // LDS.128 costs two wavefronts of the pipe that bounds this kernel
+      for (int q = 0; q < 8; ++q) {
+        const float4 bv = *reinterpret_cast<const float4*>(s_bias + l * 64 + half * 32 + q * 4);
+        bias_r[4 * q] = bv.x; bias_r[4 * q + 1] = bv.y; bias_r[4 * q + 2] = bv.z; bias_r[4 * q + 3] = bv.w;
+      }
       for (int t = 0; t < nt; ++t) {
         const int m = t * 128 + row_in_tile;
         const int bi = m / Ge::BS, rem = m % Ge::BS, r = rem / Ge::W8, c = rem % Ge::W8;
@@ -705,11 +715,8 @@ k_eval_umma(const uint8_t* __restrict__ image, const EvalWork W, const Trees T, 
 #pragma unroll
         for (int j = 0; j < 4; ++j) {                               // one 8-channel chunk = one 16-B store
           float v[8];
-          const float4 b0 = *reinterpret_cast<const float4*>(bias_l + j * 8), b1 = *reinterpret_cast<const float4*>(bias_l + j * 8 + 4);
-          v[0] = __uint_as_float(a[j * 8 + 0]) + b0.x; v[1] = __uint_as_float(a[j * 8 + 1]) + b0.y;
-          v[2] = __uint_as_float(a[j * 8 + 2]) + b0.z; v[3] = __uint_as_float(a[j * 8 + 3]) + b0.w;
-          v[4] = __uint_as_float(a[j * 8 + 4]) + b1.x; v[5] = __uint_as_float(a[j * 8 + 5]) + b1.y;
-          v[6] = __uint_as_float(a[j * 8 + 6]) + b1.z; v[7] = __uint_as_float(a[j * 8 + 7]) + b1.w;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(a[j * 8 + e]) + bias_r[j * 8 + e];
           if (has_skip) {
             v[0] += bf_lo(sk[j].x); v[1] += bf_hi(sk[j].x); v[2] += bf_lo(sk[j].y); v[3] += bf_hi(sk[j].y);
             v[4] += bf_lo(sk[j].z); v[5] += bf_hi(sk[j].z); v[6] += bf_lo(sk[j].w); v[7] += bf_hi(sk[j].w);
@@ -797,7 +804,7 @@ k_eval_umma(const uint8_t* __restrict__ image, const EvalWork W, const Trees T, 
       constexpr int P = Ge::P;
       constexpr int NOUT = G::A + 1;
       float* s_part = reinterpret_cast<float*>(smem + Sm::OFF_PART);   // [8 warps][NB][8 slots]
-      const int we = warp - 2;
+      const int we = warp - EPI_WARP0;
       const bool is_pol = et < 4 * P, is_val = !is_pol && et < 5 * P;
       const int pos = is_pol ? (et % P) : (is_val ? et - 4 * P : 0);
       const int c4 = is_pol ? (et / P) : 4;                          // position-major inside a chunk: conflict-free reads
@@ -903,7 +910,7 @@ k_eval_umma(const uint8_t* __restrict__ image, const EvalWork W, const Trees T, 
         }
       }
       // asynchronous pipeline: hand the evaluated trees to the tree warps (each lane releases the record it just wrote)
-      if (RING && warp == 2) ring_push_warp(C.ready, nb, slot, lane);
+      if (RING && warp == EPI_WARP0) ring_push_warp(C.ready, nb, slot, lane);
       TRACE2(4);
       epi_bar_sync();                                               // s_logits is reused by the next batch; buffer 0 by layer 1
       TRACE2(5);
@@ -936,19 +943,18 @@ k_eval_umma(const uint8_t* __restrict__ image, const EvalWork W, const Trees T, 
     }
   }
 
-#if defined(SPB_SPLIT_CTAS)
-  // experiment: the last SPB_SPLIT_CTAS CTAs are tree-only (all 16 warps), the others evaluator-only
-  if (RING && blockIdx.x + SPB_SPLIT_CTAS >= gridDim.x) tree_worker<G>(T, C, lane);
-#elif defined(SPB_SKIP_SCHED1)
-  if (RING && warp > STAGER_WARP && (warp & 3) != 1) tree_worker<G>(T, C, lane);   // experiment: no tree warp on the MMA warp's scheduler
-#else
-  if (RING && warp > STAGER_WARP) tree_worker<G>(T, C, lane);       // warps 11+: the tree side of the pipeline (async.cuh)
-#endif
+  if (RING && warp >= EPI_WARP0 + N_EPI_WARPS) {
+    // ===== warps 12..15: the tree side of the pipeline (async.cuh) ====================================
+    SPB_REGS_TREE();
+    tree_worker<G>(T, C, lane);
+  } else if (RING && warp == SPARE_WARP) {
+    SPB_REGS_LIGHT();                                               // its warpgroup's registers go to the epilogue warps
+  }
 
   // ---- teardown -----------------------------------------------------------------------------------
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+  if (warp == MMA_WARP) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 #ifdef SPB_TRACE
   if (blockIdx.x == 0 && tid == 0) {
     const unsigned int i = g_eval_idx++ & 63u;
