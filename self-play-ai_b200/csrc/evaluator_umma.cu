@@ -351,7 +351,7 @@ struct Smem {
   static constexpr int OFF_BARS = (OFF_SLOTS + 2 * Ge::NB * 4 + 15) & ~15;
   // barriers: w_full[9], w_empty[9], acc_full[4], act_ready[4], stage_ready[4], acc_full of odd batches [4], act0_free,
   // head_drained[4], batch[2], claim_go
-  static constexpr int N_BARS = 2 * N_SLOTS + 5 * Ge::NT + 1 + 3;
+  static constexpr int N_BARS = 2 * N_SLOTS + 5 * Ge::NT + 1 + 3 + 2;   // ... + out_ready, out_free
   static constexpr int OFF_TMEM = OFF_BARS + N_BARS * 8;
   static constexpr int OFF_NB = OFF_TMEM + 16;                     // [4] boards of batch bb (0 = no more batches), [4] = early flag
   static constexpr int TOTAL = OFF_NB + 32;
@@ -361,7 +361,7 @@ static_assert(Geo<Connect4>::NB <= 32 && Geo<TicTacToe>::NB <= 32, "one stager l
 static_assert(Smem<Connect4>::TOTAL <= 232448 && Smem<TicTacToe>::TOTAL <= 232448, "shared memory plan exceeds 227 KB");
 // Warp roles.  The eight epilogue warps are warps 4..11 = warpgroups 1 and 2, so that the asynchronous kernel can move
 // registers to them with setmaxnreg (a warpgroup-wide instruction); a warp's TMEM lane quadrant is warp % 4.
-constexpr int PRODUCER_WARP = 0, MMA_WARP = 1, STAGER_WARP = 2, SPARE_WARP = 3;   // warp 3 only completes warpgroup 0
+constexpr int PRODUCER_WARP = 0, MMA_WARP = 1, STAGER_WARP = 2, SPARE_WARP = 3;   // warp 3: publisher of the results
 constexpr int EPI_WARP0 = 4, N_EPI_WARPS = 8;
 constexpr int THREADS = 32 * (EPI_WARP0 + N_EPI_WARPS);   // 384: static work list (spb_predict, lock-step pipeline)
 constexpr int TREE_WARPS = 4;    // asynchronous pipeline: warps 12..15 (warpgroup 3),: tree warps that share the CTA (and the SM's idle issue slots)
@@ -441,6 +441,10 @@ k_eval_umma(const uint8_t* __restrict__ image, const EvalWork W, const Trees T, 
   // asynchronous pipeline: the MMA warp arrives when it starts layer 7 of a batch — time for the stager to claim the next
   // batch's leaves from the ring (late enough not to hoard leaves, early enough to have them staged behind the head conv)
   const uint32_t bar_claim_go = bar_base + (uint32_t)(2 * N_SLOTS + 5 * Ge::NT + 3) * 8u;
+  // results of a batch (softmax probabilities + value per board, in s_logits) handed from the epilogue warps to the
+  // publisher warp, which writes them to global memory and (asynchronous pipeline) pushes the trees to the ready ring
+  const uint32_t bar_out_ready = bar_base + (uint32_t)(2 * N_SLOTS + 5 * Ge::NT + 4) * 8u;
+  const uint32_t bar_out_free = bar_base + (uint32_t)(2 * N_SLOTS + 5 * Ge::NT + 5) * 8u;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + Sm::OFF_TMEM);
   volatile uint32_t* s_nb = reinterpret_cast<volatile uint32_t*>(smem + Sm::OFF_NB);
 
@@ -460,6 +464,7 @@ k_eval_umma(const uint8_t* __restrict__ image, const EvalWork W, const Trees T, 
     mbar_init(bar_act0_free, 1);
     for (int t = 0; t < Ge::NT; ++t) mbar_init(bar_head_drained(t), 256);
     mbar_init(bar_batch(0), 1); mbar_init(bar_batch(1), 1); mbar_init(bar_claim_go, 1);
+    mbar_init(bar_out_ready, 1); mbar_init(bar_out_free, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == MMA_WARP) tmem_alloc(smem_u32(tmem_slot), 512);
@@ -799,32 +804,46 @@ k_eval_umma(const uint8_t* __restrict__ image, const EvalWork W, const Trees T, 
     // the last policy output).  Per board: ONE 16-byte shared-memory read per thread (the tensor pipe needs the
     // shared-memory bandwidth), 8 slot partials, a 7-shuffle transposing reduction inside the warp, then the 8 warp
     // partials are added in warp order.  The summation order of a board is fixed, whatever the batch looks like.
-    auto linear_heads = [&](uint32_t bb) {
+    // The Linear layers' geometry of this thread: one unit = (position, 8-channel chunk) of the head activations.
+    constexpr int LH_P = Ge::P;
+    constexpr int NOUT = G::A + 1;
+    const bool is_pol = et < 4 * LH_P, is_val = !is_pol && et < 5 * LH_P;
+    const int pos = is_pol ? (et % LH_P) : (is_val ? et - 4 * LH_P : 0);
+    const int c4 = is_pol ? (et / LH_P) : 4;                         // position-major inside a chunk: conflict-free reads
+    // the unit's weights for the 8 output slots og..og+7 (policy outputs, the value right after the last policy output)
+    auto load_head_weights = [&](float (&w)[8][8], int og) {
+#pragma unroll
+      for (int s = 0; s < 8; ++s) {
+        const int o = og + s;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) w[s][j] = 0.0f;
+        const float* src = nullptr;
+        if (is_pol && o < G::A) src = g_wp + ((size_t)o * LH_P + pos) * NET_POLICY_CH + c4 * 8;
+        if (is_val && o == G::A) src = g_wv + pos * 8;
+        if (src) {
+          const float4 w0 = __ldg(reinterpret_cast<const float4*>(src)), w1 = __ldg(reinterpret_cast<const float4*>(src) + 1);
+          w[s][0] = w0.x; w[s][1] = w0.y; w[s][2] = w0.z; w[s][3] = w0.w;
+          w[s][4] = w1.x; w[s][5] = w1.y; w[s][6] = w1.z; w[s][7] = w1.w;
+        }
+      }
+    };
+    // w_first: the weights of the first output group, loaded by the caller before the head conv's epilogue so that their
+    // latency is off the critical path (the Linear layers sit between the stem and layer 1 of the next batch).
+    auto linear_heads = [&](uint32_t bb, float (&w_first)[8][8]) {
       const uint32_t nb = s_nb[bb & 3u];
-      constexpr int P = Ge::P;
-      constexpr int NOUT = G::A + 1;
       float* s_part = reinterpret_cast<float*>(smem + Sm::OFF_PART);   // [8 warps][NB][8 slots]
       const int we = warp - EPI_WARP0;
-      const bool is_pol = et < 4 * P, is_val = !is_pol && et < 5 * P;
-      const int pos = is_pol ? (et % P) : (is_val ? et - 4 * P : 0);
-      const int c4 = is_pol ? (et / P) : 4;                          // position-major inside a chunk: conflict-free reads
       const uint32_t roff = (uint32_t)((is_pol || is_val ? (2 + c4) * Ge::Q * 16 : 0) + ((pos / G::COLS) * Ge::W8 + (pos % G::COLS)) * 16);
       TRACE2(0);
       for (int og = 0; og < NOUT; og += 8) {
         float w[8][8];
+        if (og == 0) {
 #pragma unroll
-        for (int s = 0; s < 8; ++s) {
-          const int o = og + s;
+          for (int s = 0; s < 8; ++s)
 #pragma unroll
-          for (int j = 0; j < 8; ++j) w[s][j] = 0.0f;
-          const float* src = nullptr;
-          if (is_pol && o < G::A) src = g_wp + ((size_t)o * P + pos) * NET_POLICY_CH + c4 * 8;
-          if (is_val && o == G::A) src = g_wv + pos * 8;
-          if (src) {
-            const float4 w0 = __ldg(reinterpret_cast<const float4*>(src)), w1 = __ldg(reinterpret_cast<const float4*>(src) + 1);
-            w[s][0] = w0.x; w[s][1] = w0.y; w[s][2] = w0.z; w[s][3] = w0.w;
-            w[s][4] = w1.x; w[s][5] = w1.y; w[s][6] = w1.z; w[s][7] = w1.w;
-          }
+            for (int j = 0; j < 8; ++j) w[s][j] = w_first[s][j];
+        } else {
+          load_head_weights(w, og);
         }
         TRACE2(1);
         const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
@@ -877,6 +896,7 @@ k_eval_umma(const uint8_t* __restrict__ image, const EvalWork W, const Trees T, 
         }
         TRACE2(2);
         epi_bar_sync();
+        if (og == 0 && bb > 0) mbar_wait(bar_out_free, (bb - 1) & 1u);   // the publisher has read the previous batch's results
         for (int i = et; i < (int)nb * 8; i += 256) {
           const int bi = i >> 3, s = i & 7, o = og + s;
           if (o < NOUT) {
@@ -889,9 +909,7 @@ k_eval_umma(const uint8_t* __restrict__ image, const EvalWork W, const Trees T, 
         epi_bar_sync();
       }
       TRACE2(3);
-      uint32_t slot = 0;
       if ((uint32_t)et < nb) {                                      // one thread per board
-        slot = s_slots[(bb & 1u) * Ge::NB + et];
         const float* fcb = s_bias + N_LAYERS * 64;
         float lg[G::A];
         float mx = -INFINITY;
@@ -900,19 +918,21 @@ k_eval_umma(const uint8_t* __restrict__ image, const EvalWork W, const Trees T, 
         float ex[G::A], sum = 0.0f;
 #pragma unroll
         for (int a = 0; a < G::A; ++a) { ex[a] = expf(lg[a] - mx); sum += ex[a]; }
-        float* o = out + (size_t)slot * stride;
+        const float val = tanhf(s_logits[et * 16 + 15] + fcb[16]);
+        // the board's record (softmax probabilities, value) replaces its logits in s_logits: the publisher warp writes it to
+        // global memory, so that the global stores and the release of the trees are not on the epilogue warps' path
 #pragma unroll
-        for (int a = 0; a < G::A; ++a) o[a] = ex[a] / sum;
-        o[G::A] = tanhf(s_logits[et * 16 + 15] + fcb[16]);
-        if (logits_out) {
+        for (int a = 0; a < G::A; ++a) s_logits[et * 16 + a] = ex[a] / sum;
+        s_logits[et * 16 + 15] = val;
+        if (logits_out) {                                           // spb_predict(raw_logits) only
+          const uint32_t slot = s_slots[(bb & 1u) * Ge::NB + et];
 #pragma unroll
           for (int a = 0; a < G::A; ++a) logits_out[(size_t)slot * G::A + a] = lg[a];
         }
       }
-      // asynchronous pipeline: hand the evaluated trees to the tree warps (each lane releases the record it just wrote)
-      if (RING && warp == EPI_WARP0) ring_push_warp(C.ready, nb, slot, lane);
       TRACE2(4);
-      epi_bar_sync();                                               // s_logits is reused by the next batch; buffer 0 by layer 1
+      epi_bar_sync();                                               // the records are complete; buffer 0 is free for layer 1
+      if (et == 0) mbar_arrive(bar_out_ready);
       TRACE2(5);
     };
 
@@ -921,6 +941,8 @@ k_eval_umma(const uint8_t* __restrict__ image, const EvalWork W, const Trees T, 
     if (nb_cur != 0u) conv_epilogue(0, 0);
     for (uint32_t b = 0; nb_cur != 0u; ++b) {
       for (int l = 1; l < 9; ++l) conv_epilogue(b, l);
+      float w_heads[8][8];
+      load_head_weights(w_heads, 0);                                // in flight during the head conv's epilogue
       head_epilogue(b);
       // Has the stager already decided the next batch?  One thread looks, so that all 256 epilogue threads take the
       // same branch (both branches contain named barriers).
@@ -931,11 +953,11 @@ k_eval_umma(const uint8_t* __restrict__ image, const EvalWork W, const Trees T, 
         // The stem of the next batch ran on the tensor pipe behind this batch's head conv (the stager had its input
         // ready): release layer 1 of the next batch before spending time on this batch's Linear layers.
         if (nb_next != 0u) conv_epilogue(b + 1, 0);
-        linear_heads(b);
+        linear_heads(b, w_heads);
       } else {
         // The next batch is not known yet (few leaves in flight): its leaves may depend on THIS batch's results, so the
         // results go out first.
-        linear_heads(b);
+        linear_heads(b, w_heads);
         nb_next = wait_batch(b + 1);
         if (nb_next != 0u) conv_epilogue(b + 1, 0);
       }
@@ -947,8 +969,33 @@ k_eval_umma(const uint8_t* __restrict__ image, const EvalWork W, const Trees T, 
     // ===== warps 12..15: the tree side of the pipeline (async.cuh) ====================================
     SPB_REGS_TREE();
     tree_worker<G>(T, C, lane);
-  } else if (RING && warp == SPARE_WARP) {
-    SPB_REGS_LIGHT();                                               // its warpgroup's registers go to the epilogue warps
+  } else if (warp == SPARE_WARP) {
+    // ===== warp 3: publisher.  Writes the records of a finished batch (out[slot] = softmax probabilities + value) and, in
+    // the asynchronous pipeline, hands the evaluated trees to the tree warps through the ready ring. =====================
+    SPB_REGS_LIGHT();
+    const float* s_logits = reinterpret_cast<const float*>(smem + Sm::OFF_LOGITS);
+    const uint32_t* s_slots = reinterpret_cast<const uint32_t*>(smem + Sm::OFF_SLOTS);
+    for (uint32_t b = 0;; ++b) {
+      const uint32_t nb = wait_batch(b);
+      if (nb == 0u) break;
+      mbar_wait(bar_out_ready, b & 1u);
+      uint32_t slot = 0;
+      float rec[G::A + 1];
+      if ((uint32_t)lane < nb) {
+        slot = s_slots[(b & 1u) * Ge::NB + lane];
+#pragma unroll
+        for (int a = 0; a < G::A; ++a) rec[a] = s_logits[lane * 16 + a];
+        rec[G::A] = s_logits[lane * 16 + 15];
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_out_free);
+      if ((uint32_t)lane < nb) {
+        float* o = out + (size_t)slot * stride;
+#pragma unroll
+        for (int a = 0; a <= G::A; ++a) o[a] = rec[a];
+      }
+      if (RING) ring_push_warp(C.ready, nb, slot, lane);            // each lane releases the record it just wrote
+    }
   }
 
   // ---- teardown -----------------------------------------------------------------------------------
