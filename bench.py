@@ -3,6 +3,8 @@
 
     python bench.py --gpus N --steps K --warmup W          # this framework, one rank per GPU
     python bench.py --impl reference ...                   # the reference's algorithm on the host CPU cores
+    python bench.py --leaves 16                            # configs[3]: 16 leaves in flight per tree (virtual loss, lock-step)
+    python bench.py --game ttt --sims 600                  # configs[0]: tic-tac-toe
 
 One "step" = one `search` call (ref: Mcts::search, src/mcts.rs:196) of 800 simulations over 4,096 concurrent
 Connect4 games per GPU, every tree fresh at a seeded synthetic root, evaluator = the
@@ -13,10 +15,13 @@ fixed (weak scaling); `value` is the whole-job aggregate.
             max over ranks.
   e2e       the same metric through the C ABI with HOST buffers: spb_reset_games (H2D) + spb_search +
             spb_root_children_all (D2H) per step, wall clock between synchronisations, max over ranks.
-  roofline  the dominant kernel (the fused tcgen05 evaluator): FLOPs per launch / average launch duration
-            measured live with CUDA events, against the measured bf16 peak of MEASURED_PEAKS.json.
-  cpu_baseline  the C++ restatement of the reference (oracle/) with the torch CPU fp32 net, all host cores,
-            on a bounded sample of the same workload (rank 0, N = 1 only).
+  roofline  the dominant kernel.  Default (asynchronous pipeline): ONE resident kernel per search that holds the tcgen05
+            evaluator and the tree warps; achieved = evaluated positions x FLOPs per position / the search's device time
+            (CUDA events on the engine's stream), against the measured sustained bf16 peak of MEASURED_PEAKS.json.
+            `traffic` is read from the committed ncu summary of that kernel (profiles/, named in the line).
+  cpu_baseline  the C++ restatement of the reference (oracle/) with the torch CPU fp32 net, one PROCESS per host core
+            (the reference's workers share nothing: src/main.rs:169), 100 games each, one full 800-simulation search
+            (rank 0, N = 1 only).
 """
 from __future__ import annotations
 
@@ -35,8 +40,35 @@ if ROOT not in sys.path:
 GAMES_PER_GPU = 4096
 SIMS = 800
 REF_GAMES_PER_THREAD = 100        # learner_concurrent.rs:56 num_batched_self_play_games
+REF_SEGMENT = 100                 # the CPU arm's step: 100 consecutive simulations of an 800-simulation search
 METRIC = "MCTS simulations/sec (whole box) Connect4 @800 sims/move"
 WORKLOAD = "connect4_6x7_batched_selfplay_4096_games_x_800_sims_per_gpu"
+NCU_SUMMARY = os.path.join("profiles", "r02_ncu_eval_async_summary.json")   # source of roofline.traffic
+
+
+def workload_name(game, games, sims, leaves):
+    if game == "ttt":
+        return "tictactoe_3x3_selfplay_%d_games_x_%d_sims_per_gpu" % (games, sims)
+    if leaves > 1:
+        return "connect4_6x7_parallel_tree_search_virtual_loss_%d_leaves_per_tree_%d_games_x_%d_sims_per_gpu" % (leaves, games, sims)
+    if (games, sims) == (GAMES_PER_GPU, SIMS):
+        return WORKLOAD
+    return "connect4_6x7_batched_selfplay_%d_games_x_%d_sims_per_gpu" % (games, sims)
+
+
+def metric_name(game, sims):
+    return METRIC if (game, sims) == ("c4", SIMS) else "MCTS simulations/sec (whole box) %s @%d sims/move" % (
+        "Connect4" if game == "c4" else "tic-tac-toe", sims)
+
+
+def ncu_traffic():
+    """DRAM bytes (read + write) per launch of the dominant kernel, from the committed `ncu --set full` summary."""
+    try:
+        with open(os.path.join(ROOT, NCU_SUMMARY)) as f:
+            j = json.load(f)
+        return j.get("traffic_bytes_per_launch"), NCU_SUMMARY
+    except Exception:
+        return None, None
 
 
 def _peaks():
@@ -97,54 +129,91 @@ class ClockSampler:
 # -------------------------------------------------------------------------------------------------
 # reference arm / CPU baseline: the oracle (C++ restatement of mcts.rs + connect_four.rs) with the torch CPU net
 # -------------------------------------------------------------------------------------------------
-def cpu_reference_run(num_searches: int, threads: int | None = None, repeats: int = 1, warmup: int = 0, blob: bytes | None = None):
-    """T worker threads, each an independent `search` over its own 100 games (the shape of main.rs:169's
-    SelfPlayWorkers), evaluator = torch CPU fp32 forward of the same weights, 1 intra-op thread per worker.
-    Returns list of (sims, seconds) per repeat."""
-    import numpy as np
-    import torch
+class CpuArm:
+    """The reference's self-play workers on the host cores: one process per worker (oracle/cpu_worker.py), each an
+    independent `search` over its own 100 games (learner_concurrent.rs:56) with its own copy of the net — the shape of
+    main.rs:169's SelfPlayWorkers.  A step = `segment` consecutive simulations; the trees persist until `sims` simulations
+    have been run on them (one full search), then every worker starts fresh trees."""
 
-    from oracle import pyoracle as O
-    from oracle import torch_net
-    from selfplay_b200.weights_init import random_checkpoint
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    from helpers import synthetic_roots
+    def __init__(self, game: str, sims: int, blob: bytes, workers: int | None = None, segment: int = REF_SEGMENT):
+        import tempfile
+        self.workers = workers or (os.cpu_count() or 1)
+        self.sims, self.segment = sims, min(segment, sims)
+        self.done_on_trees = 0
+        self.tmp = tempfile.NamedTemporaryFile(suffix=".safetensors", delete=False)
+        self.tmp.write(blob)
+        self.tmp.close()
+        gid = 1 if game == "c4" else 0
+        env = dict(os.environ, OMP_NUM_THREADS="1", MKL_NUM_THREADS="1")
+        self.procs = [subprocess.Popen([sys.executable, os.path.join(ROOT, "oracle", "cpu_worker.py"), str(gid), str(w),
+                                        str(REF_GAMES_PER_THREAD), self.tmp.name], stdin=subprocess.PIPE, stdout=subprocess.PIPE,
+                                       stderr=subprocess.DEVNULL, text=True, env=env) for w in range(self.workers)]
+        for p in self.procs:
+            if p.stdout.readline().strip() != "ready":
+                raise RuntimeError("CPU worker failed to start")
 
-    threads = threads or (os.cpu_count() or 1)
-    torch.set_num_threads(1)
-    net = torch_net.load_tch_safetensors(blob or random_checkpoint(1, 0), 1)
-    roots = synthetic_roots(O.GAME_C4, threads * REF_GAMES_PER_THREAD)
+    def _all(self, cmd):
+        for p in self.procs:
+            p.stdin.write(cmd + "\n")
+            p.stdin.flush()
+        return [p.stdout.readline().split() for p in self.procs]
 
-    def fn(enc):
-        p, v, _ = torch_net.forward_probs(net, np.array(enc, copy=True))
-        return p, v
+    def step(self):
+        """-> (simulations, evaluations, terminal leaves, wall seconds) of one step over all workers."""
+        if self.done_on_trees >= self.sims:
+            self._all("reset")                                   # Tree::with_root_state: next search, untimed
+            self.done_on_trees = 0
+        n = min(self.segment, self.sims - self.done_on_trees)
+        t0 = time.perf_counter()
+        rep = self._all("step %d" % n)
+        dt = time.perf_counter() - t0
+        self.done_on_trees += n
+        return sum(int(r[0]) for r in rep), sum(int(r[1]) for r in rep), sum(int(r[2]) for r in rep), dt
 
-    cb = O.make_eval_callback(O.GAME_C4, fn)
-    out = []
-    for r in range(warmup + repeats):
-        sims, sec = O.baseline_run(O.GAME_C4, roots, threads, REF_GAMES_PER_THREAD, num_searches, evaluator=O.EVAL_NET, callback=cb)
-        if r >= warmup:
-            out.append((sims, sec))
-    return out, threads
+    def sample(self):
+        return ("%d worker processes x %d games, each step = %d consecutive simulations of a %d-simulation search (trees persist for "
+                "%d steps, then fresh trees at the same seeded roots); torch CPU fp32 evaluator, 1 intra-op thread per worker" % (
+                    self.workers, REF_GAMES_PER_THREAD, self.segment, self.sims, -(-self.sims // self.segment)))
+
+    def close(self):
+        for p in self.procs:
+            try:
+                p.stdin.write("quit\n")
+                p.stdin.flush()
+            except Exception:
+                pass
+        for p in self.procs:
+            try:
+                p.wait(timeout=10)
+            except Exception:
+                p.kill()
+        os.unlink(self.tmp.name)
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0                                          # rank 0 alone runs the CPU arm
-    sims_per_step = args.ref_sims
-    runs, threads = cpu_reference_run(sims_per_step, repeats=args.steps, warmup=args.warmup)
-    total_sims = sum(s for s, _ in runs)
-    total_sec = sum(t for _, t in runs)
-    value = total_sims / total_sec
-    sample = "%d threads x %d games x %d sims per step (same seeded roots, torch CPU fp32 evaluator, 1 intra-op thread per worker)" % (
-        threads, REF_GAMES_PER_THREAD, sims_per_step)
+    from selfplay_b200.weights_init import random_checkpoint
+    arm = CpuArm(args.game, args.sims, random_checkpoint(1 if args.game == "c4" else 0, 0), segment=args.ref_segment)
+    tot = [0, 0, 0, 0.0]
+    try:
+        for i in range(args.warmup + args.steps):
+            r = arm.step()
+            if i >= args.warmup:
+                tot = [a + b for a, b in zip(tot, r)]
+    finally:
+        sample = arm.sample()
+        threads = arm.workers
+        arm.close()
+    value = tot[0] / tot[3]
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": "sims/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * total_sec / max(1, len(runs)), "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": metric_name(args.game, args.sims), "value": value, "unit": "sims/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * tot[3] / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "reference_arm": "oracle port of src/mcts.rs + src/game/connect_four.rs (the Rust crate cannot be built here: no rustc/cargo), evaluator = torch CPU fp32",
-                   "sample": sample},
+        "config": {"workload": workload_name(args.game, args.games, args.sims, 1),
+                   "reference_arm": "oracle port of src/mcts.rs + src/game/*.rs (the Rust crate cannot be built here: no rustc/cargo), evaluator = torch CPU fp32",
+                   "sample": sample, "terminal_leaf_fraction": tot[2] / max(1, tot[0])},
         "cpu_baseline": {"value": value, "unit": "sims/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "sims/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -175,15 +244,18 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200; there is no CPU fallback (use --impl reference for the CPU arm)")
 
-    G, sims = args.games, args.sims
-    blob = random_checkpoint(1, 0)
+    G, sims, K = args.games, args.sims, args.leaves
+    game = S.GAME_C4 if args.game == "c4" else S.GAME_TTT
+    A_branch = 7 if args.game == "c4" else 9
+    blob = random_checkpoint(1 if args.game == "c4" else 0, 0)
     # node pools sized for the full-game leg (a tree can carry nearly all of its nodes through a re-root and adds at most
-    # 7 per simulation), so that no pool growth (spb_search widens the pools on demand) lands inside a timed region
-    eng = S.Engine(game=S.GAME_C4, num_games=G, evaluator=S.EVAL_NET, device=local_rank,
+    # A per simulation), so that no pool growth (spb_search widens the pools on demand) lands inside a timed region
+    eng = S.Engine(game=game, num_games=G, evaluator=S.EVAL_NET, device=local_rank, leaves_per_tree=K,
                    game_id_base=rank * G, game_id_stride=world * G,
-                   max_nodes_per_tree=1024 * ((7 * sims * (args.full_game_moves + 1) + 1024) // 1024))
+                   max_nodes_per_tree=1024 * ((A_branch * sims * (args.full_game_moves + 1) + 1024) // 1024))
     eng.load_weights(blob)
-    roots = synthetic_roots_device(eng, G, start=rank * G)       # games are sharded by rank: rank r owns ids [r*G, (r+1)*G)
+    # games are sharded by rank: rank r owns ids [r*G, (r+1)*G)
+    roots = synthetic_roots_device(eng, G, start=rank * G, max_ply=21 if args.game == "c4" else 5)
 
     def barrier():
         if world > 1:
@@ -209,6 +281,7 @@ def run_ours(args):
     eng.reset_counters()
     barrier()
     dev_ms, t0 = 0.0, time.perf_counter()
+    stats = None
     for _ in range(args.steps):
         eng.reset_games(roots)            # untimed part of `value`: fresh trees; roots then live in HBM
         eng.search(sims)                  # synchronous; its device time is measured with CUDA events inside
@@ -216,6 +289,7 @@ def run_ours(args):
     barrier()
     wall_s = time.perf_counter() - t0
     ctr = eng.counters()
+    stats = eng.async_stats()
     launches = ctr["kernel_launches"]
     dev_ms = rank_max(dev_ms)
     wall_s = rank_max(wall_s)
@@ -232,41 +306,57 @@ def run_ours(args):
     clocks = sampler.stop()
     h2d = G * 16
     d2h = G * (2 * 4 * S.MAX_ACTIONS + 4 + S.MAX_ACTIONS)
-    assert int(counts[0].sum()) == sims - 1
+    assert int(counts[0].sum()) == sims - (K if K > 1 else 1)
 
-    # ---- roofline of the dominant kernel (evaluator), measured live -----------------------------------
-    eval_ms, n_pos, flops_pos = eng.time_evaluator(iters=30)
+    # ---- roofline of the dominant kernel, measured live ------------------------------------------------
     peak_tf, peak_hbm, peak_src = _peaks()
-    achieved_tf = flops_pos * n_pos / (eval_ms * 1e-3) / 1e12
     total_sims = world * G * sims * args.steps
     value = total_sims / (dev_ms * 1e-3)
     D = ctr["path_length_sum"] / max(1, ctr["simulations"])
     bbar = ctr["children_created"] / max(1, ctr["evaluations"])
     tree_bytes_per_sim = 16 * bbar * D + 36 * bbar + 16 * D + 96
-    evals_per_step = ctr["evaluations"] / args.steps / sims
-    step_us = dev_ms * 1e3 / args.steps / sims
-    tree_us = max(1e-9, step_us - eval_ms * 1e3 * (evals_per_step / max(1, n_pos)))
-
+    static_ms, static_n, flops_pos = eng.time_evaluator(iters=10)            # also: FLOPs per position
+    if K == 1:
+        # asynchronous pipeline: one resident kernel per search = evaluator CTAs + tree warps.  Its duration is the search's
+        # device time (the ring reset and the queueing kernel in front of it take microseconds).
+        evals_per_launch = ctr["evaluations"] / args.steps
+        launch_ms = dev_ms / args.steps
+        kernel = "umma::k_eval_umma<%s, RING=true> (resident: tcgen05 evaluator + tree warps)" % ("Connect4" if args.game == "c4" else "TicTacToe")
+        traffic, traffic_src = ncu_traffic() if (args.game, G, sims) == ("c4", GAMES_PER_GPU, SIMS) else (None, None)
+    else:
+        evals_per_launch, launch_ms = static_n, static_ms
+        kernel = "umma::k_eval_umma<Connect4, RING=false> (one launch per lock-step, %d leaves per tree)" % K
+        traffic, traffic_src = None, None
+    achieved_tf = flops_pos * evals_per_launch / (launch_ms * 1e-3) / 1e12
+    roof = {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
+            "traffic": traffic, "traffic_source": traffic_src, "kernel": kernel, "peak_source": peak_src,
+            "positions_per_launch": evals_per_launch, "flops_per_position": flops_pos, "avg_launch_ms": launch_ms,
+            "static_list_launch": {"positions": static_n, "ms": static_ms,
+                                   "tflops": flops_pos * static_n / (static_ms * 1e-3) / 1e12,
+                                   "note": "the same evaluator on one static list (spb_predict / lock-step shape), timed alone"}}
     line = {
-        "metric": METRIC, "value": value, "unit": "sims/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "metric": metric_name(args.game, sims), "value": value, "unit": "sims/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": WORKLOAD if (G, sims) == (GAMES_PER_GPU, SIMS) else "connect4_%d_games_x_%d_sims_per_gpu" % (G, sims),
-                   "games_per_gpu": G, "sims_per_move": sims, "evaluator": "connect4 4x64 conv ResNet, random init (numpy seed 0), BN folded",
+        "config": {"workload": workload_name(args.game, G, sims, K),
+                   "games_per_gpu": G, "sims_per_move": sims, "leaves_per_tree": K,
+                   "pipeline": "asynchronous (trees and leaves circulate between tree warps and resident evaluator CTAs)" if K == 1 else "lock-step with virtual loss",
+                   "evaluator": "%s 4x64 conv ResNet, random init (numpy seed 0), BN folded" % ("connect4" if args.game == "c4" else "tic-tac-toe"),
                    "parallelism": "games sharded by rank, no collective on the search path",
                    "cache": "inputs larger than L2: per-GPU node pools touched per step ~%d MB" % (ctr["nodes_live"] * 20 // (1 << 20)),
                    "timing": "CUDA events on the engine stream around each search, max over ranks; wall clock %.3f s" % wall_s},
         "e2e": {"value": total_sims / e2e_s, "unit": "sims/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
-                     "traffic": 849152, "kernel": "umma_v2::k_eval_umma<Connect4>", "peak_source": peak_src,
-                     "positions_per_launch": n_pos, "flops_per_position": flops_pos, "avg_launch_ms": eval_ms},
-        "roofline_tree": {"bound": "hbm", "unit": "GB/s", "peak": peak_hbm, "bytes_per_sim": tree_bytes_per_sim, "mean_path_length": D,
-                          "mean_branching": bbar, "tree_us_per_step": tree_us,
-                          "achieved": tree_bytes_per_sim * G / (tree_us * 1e-6) / 1e9,
-                          "frac": tree_bytes_per_sim * G / (tree_us * 1e-6) / 1e9 / peak_hbm},
+        "roofline": roof,
+        "tree_side": {"bytes_per_sim_algorithmic": tree_bytes_per_sim, "mean_path_length": D, "mean_branching": bbar,
+                      "algorithmic_gbs": tree_bytes_per_sim * G * sims * args.steps / (dev_ms * 1e-3) / 1e9, "hbm_peak_gbs": peak_hbm,
+                      "tree_warps": stats["tree_warps"], "tree_warp_busy_frac": stats["tree_busy_ns"] / max(1, stats["tree_warps"]) / max(1e-9, eng.last_search_timing()[0] * 1e6),
+                      "us_per_tree_visit": stats["tree_busy_ns"] / max(1, stats["tree_visits"]) / 1e3,
+                      "boards_per_evaluator_batch": stats["boards"] / max(1, stats["batches"]),
+                      "note": "latency-bound pointer chasing that runs under the evaluator in the same kernel; statistics of the last search (spb_last_async_stats)"},
         "counters": {k: ctr[k] for k in ("simulations", "evaluations", "terminal_leaves")},
+        "terminal_leaf_fraction": ctr["terminal_leaves"] / max(1, ctr["simulations"]),
     }
     # ---- full-game leg: greedy last-max moves, subtree reuse, finished slots refilled from the same roots ------
     if args.full_game_moves > 0:
@@ -284,13 +374,20 @@ def run_ours(args):
         line["full_game"] = {"moves": args.full_game_moves, "value": world * G * sims * args.full_game_moves / fg_s, "unit": "sims/s",
                              "finished_games_rank0": int(finished), "trajectory_positions_rank0": int(len(pos)),
                              "note": "search + on-device move selection + use_subtree per move, wall clock"}
-    # ---- CPU baseline beside it (rank 0, N = 1 only; bounded sample) -----------------------------------
+    # ---- CPU baseline beside it (rank 0, N = 1 only): ONE full search of `sims` simulations on every host core ----------
     if world == 1 and not args.no_cpu_baseline:
         eng.close()
-        runs, threads = cpu_reference_run(args.ref_sims, repeats=1, warmup=0, blob=blob)
-        s, t = runs[0]
-        line["cpu_baseline"] = {"value": s / t, "unit": "sims/s", "cores": threads, "kind": "port",
-                                "sample": "%d threads x %d games x %d sims, same seeded roots and weights, torch CPU fp32 evaluator" % (threads, REF_GAMES_PER_THREAD, args.ref_sims)}
+        arm = CpuArm(args.game, sims, blob, segment=args.ref_segment)
+        tot = [0, 0, 0, 0.0]
+        try:
+            for _ in range(-(-sims // arm.segment)):
+                tot = [a + b for a, b in zip(tot, arm.step())]
+        finally:
+            sample, threads = arm.sample(), arm.workers
+            arm.close()
+        line["cpu_baseline"] = {"value": tot[0] / tot[3], "unit": "sims/s", "cores": threads, "kind": "port",
+                                "sample": sample + "; one full search, same seeded roots and weights as the GPU arm",
+                                "terminal_leaf_fraction": tot[2] / max(1, tot[0])}
     else:
         line["cpu_baseline"] = None
     # ---- multi-GPU: the one exchange of the path — trajectories to the learner rank -------------------
@@ -317,7 +414,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--games", type=int, default=GAMES_PER_GPU)
     ap.add_argument("--sims", type=int, default=SIMS)
-    ap.add_argument("--ref-sims", type=int, default=100, help="simulations per step of the CPU arm's bounded sample")
+    ap.add_argument("--ref-segment", type=int, default=REF_SEGMENT, help="CPU arm: simulations per step (consecutive segments of one --sims search)")
+    ap.add_argument("--leaves", type=int, default=1, help="leaves in flight per tree (configs[3]: 16); > 1 runs the lock-step virtual-loss pipeline")
+    ap.add_argument("--game", default="c4", choices=["c4", "ttt"], help="configs[0] is tic-tac-toe")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--full-game-moves", type=int, default=4, help="extra leg: self-play moves with subtree reuse (0 = skip)")
     args = ap.parse_args()

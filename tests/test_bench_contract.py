@@ -8,7 +8,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_reference_arm_prints_the_contract_line():
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--ref-sims", "3"],
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "3", "--warmup", "1", "--sims", "6", "--ref-segment", "3"],
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]
     line = json.loads(r.stdout.strip().splitlines()[-1])
@@ -19,6 +19,10 @@ def test_reference_arm_prints_the_contract_line():
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["value"] > 0
     assert "workload" in line["config"]
+    # a step is a segment of consecutive simulations of one search; the sample says so, and the arm reports how many
+    # simulations ended on a terminal node (the same statistic the GPU arm prints)
+    assert "3 consecutive simulations of a 6-simulation search" in line["config"]["sample"]
+    assert 0.0 <= line["config"]["terminal_leaf_fraction"] < 1.0
 
 
 def test_reference_arm_other_ranks_exit_quietly():
