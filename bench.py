@@ -390,15 +390,28 @@ def run_ours(args):
                                 "terminal_leaf_fraction": tot[2] / max(1, tot[0])}
     else:
         line["cpu_baseline"] = None
-    # ---- multi-GPU: the one exchange of the path — trajectories to the learner rank -------------------
+    # ---- multi-GPU: the one exchange of the path — trajectories to the learner rank over the C ABI (NCCL) -------------
     if world > 1:
-        from selfplay_b200.distributed import gather_records, gather_trajectories
-        eng.selfplay_step(S.MOVE_GREEDY_LAST_MAX)
-        gather_records(np.zeros(0, S.POSITION_DTYPE), np.zeros(0, np.uint64), dst=0)   # NCCL sets up its gather connections on first use
+        import hashlib
+        from selfplay_b200.distributed import comm_init_over_process_group
+        eng.drain_trajectories()
+        comm_init_over_process_group(eng, rank, world)
+        eng.reset_games(roots)
+        for _ in range(2):
+            eng.search(sims)
+            eng.selfplay_step(S.MOVE_GREEDY_LAST_MAX, restart_roots=roots)
+        eng.gather_trajectories(0)                               # first use sets up NCCL's connections
+        eng.search(sims)
+        eng.selfplay_step(S.MOVE_GREEDY_LAST_MAX, restart_roots=roots)
         barrier()
         t0 = time.perf_counter()
-        pos, gids = gather_trajectories(eng, dst=0)
-        line["trajectory_gather"] = {"positions": int(len(pos)) if rank == 0 else None, "seconds": time.perf_counter() - t0}
+        pos, gids = eng.gather_trajectories(0)
+        dt = time.perf_counter() - t0
+        eng.comm_destroy()
+        line["trajectory_gather"] = {"positions": int(len(pos)) if rank == 0 else None, "seconds": dt,
+                                     "sha256": hashlib.sha256(pos.tobytes() + gids.tobytes()).hexdigest() if rank == 0 else None,
+                                     "transport": "spb_gather_trajectories (C ABI): NCCL all-gather of counts + grouped send/recv, ordered by (game id, ply)",
+                                     "n_rank_equals_1_rank": "tools/gather_check.py (profiles/r02_gather_check.txt)"}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -256,6 +256,36 @@ int32_t spb_selfplay_step(spb_engine* e, int32_t rule, float temperature, uint64
 int32_t spb_drain_trajectories(spb_engine* e, spb_position* buf, size_t capacity, size_t* written,
                                uint64_t* game_ids /* nullable, [capacity] global game id per position */);
 
+/* ---- multi-GPU: trajectories to the learner rank; learner hand-off ------- */
+
+/*
+ * Games are sharded over GPUs: one engine per rank, global game ids by spb_config.game_id_base / game_id_stride, no
+ * exchange while searching.  The one exchange is the gather of finished trajectories to the learner rank — the role of the
+ * replay-buffer push of the reference's workers (ref: learner_concurrent.rs:281-288).  Transport: NCCL, bound at run time
+ * (libnccl.so.2).  Rank 0 creates an id, the host distributes its 128 bytes by any means, every rank joins:
+ */
+#define SPB_COMM_ID_BYTES 128
+int32_t spb_comm_unique_id(uint8_t* id /* [SPB_COMM_ID_BYTES] */);
+int32_t spb_comm_init(spb_engine* e, const uint8_t* id, int32_t rank, int32_t world_size);
+int32_t spb_comm_destroy(spb_engine* e);
+/*
+ * COLLECTIVE over the communicator: every rank hands over the trajectories it would otherwise return from
+ * spb_drain_trajectories (all-gather of counts, grouped send/recv into device memory of the learner rank).  On the learner
+ * rank *written = total records, ordered by (global game id, ply): the result of R ranks is byte-identical to the same
+ * games played on one rank.  If buf is NULL or capacity < *written the records stay staged and the next call (no
+ * collective) delivers them.  On the other ranks *written = 0.
+ */
+int32_t spb_gather_trajectories(spb_engine* e, int32_t learner_rank, spb_position* buf, size_t capacity, size_t* written,
+                                uint64_t* game_ids /* nullable */);
+/*
+ * ref: learner_concurrent.rs:126-146, learner.rs:162-182 — the tensors the learners train on, from n compact records
+ * (host only, no GPU needed): encodings[n][3][R][C] (get_encoding of the recorded root state, connect_four.rs:242-259),
+ * policies[n][A] (root visit counts / their sum, mcts.rs:315-328), values[n] (+-1 / 0 from the position's side to move,
+ * learner_concurrent.rs:214-226).  Any output may be NULL.
+ */
+int32_t spb_positions_to_training(int32_t game, const spb_position* positions, size_t n, float* encodings, float* policies,
+                                  float* values);
+
 /* ---- counters / timing -------------------------------------------------- */
 int32_t spb_get_counters(spb_engine* e, spb_counters* out);
 int32_t spb_reset_counters(spb_engine* e);

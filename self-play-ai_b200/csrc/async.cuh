@@ -234,6 +234,7 @@ __device__ __forceinline__ void tree_phase(const Trees& T, const AsyncCtl& C, ui
     const uint32_t pn0 = (lane < G::MAX_DEPTH) ? __ldcg(pathm + lane) : 0u;
     const uint32_t pn1 = (lane + 32 < G::MAX_DEPTH) ? __ldcg(pathm + lane + 32) : 0u;
     const uint32_t leaf = __shfl_sync(0xffffffffu, depth < 32 ? pn0 : pn1, depth & 31);
+    SPB_ASSERT(T.error, depth < G::MAX_DEPTH && (lane > depth || pn0 < n_nodes) && (lane + 32 > depth || pn1 < n_nodes), 2);
     uint2 nw0 = make_uint2(0, 0), nw1 = make_uint2(0, 0);
     if (lane <= depth) nw0 = __ldcg(reinterpret_cast<const uint2*>(&rec[pn0]));
     if (lane + 32 <= depth) nw1 = __ldcg(reinterpret_cast<const uint2*>(&rec[pn1]));
@@ -265,7 +266,8 @@ __device__ __forceinline__ void tree_phase(const Trees& T, const AsyncCtl& C, ui
     uint32_t leaf, linfo;
     int depth;
     PState st;
-    descend<G, true>(rec, root, T.c, lane, path, leaf, depth, st, linfo, T.error);
+    descend<G, true>(rec, root, T.c, lane, path, leaf, depth, st, linfo, T.error, n_nodes);
+    SPB_ASSERT(T.error, leaf < n_nodes && depth < G::MAX_DEPTH, 3);
     ctr[CTR_SIMS] += 1;
     ctr[CTR_PATHSUM] += (unsigned)depth;
     const uint32_t status = info_status(linfo);
@@ -311,6 +313,7 @@ __device__ __forceinline__ void tree_worker(const Trees& T, const AsyncCtl& C, i
     if (lane == 0) g = ready_pop_wait(C, sp);
     g = __shfl_sync(0xffffffffu, g, 0);
     if (g == RING_NONE) break;
+    SPB_ASSERT(T.error, g < T.G, 4);
     const unsigned long long t0 = gtime_ns();
     tree_phase<G>(T, C, g, lane, ctr);
     busy += gtime_ns() - t0;
@@ -337,6 +340,7 @@ __device__ __forceinline__ void builtin_eval_worker(const Trees& T, const AsyncC
     uint32_t slot = RING_NONE;
     const uint32_t k = claim_batch(C, lc, n_workers, 32u, 2000u, sp, lane, &slot);
     if (k == 0) break;
+    SPB_ASSERT(T.error, (uint32_t)lane >= k || slot < T.G * T.K, 5);
     if ((uint32_t)lane < k) {
       PState st;
       const ulonglong2 raw = __ldcg(reinterpret_cast<const ulonglong2*>(&T.leaf_state[slot]));

@@ -39,7 +39,17 @@ __host__ __device__ __forceinline__ uint32_t make_info(uint32_t fc, uint32_t nc,
 }
 
 enum CounterIdx { CTR_SIMS = 0, CTR_EVALS, CTR_TERMINAL, CTR_PATHSUM, CTR_CHILDREN, CTR_COUNT };
-enum ErrorBits : uint32_t { ERRBIT_POOL = 1u, ERRBIT_NAN = 2u };
+enum ErrorBits : uint32_t { ERRBIT_POOL = 1u, ERRBIT_NAN = 2u, ERRBIT_TRAJ_FULL = 4u, ERRBIT_BOUNDS = 8u };
+
+// Checked build (make VARIANT=-DSPB_BOUNDS_CHECK; tools/build_variant.sh check -DSPB_BOUNDS_CHECK): every index the tree,
+// ring and self-play kernels form is compared with the extent of the array it addresses; a failure sets ERRBIT_BOUNDS and
+// the site's code in bits 8..15 of the error word, and the next API call returns SPB_ERR_STATE naming it.  This is the
+// stand-in for compute-sanitizer memcheck, which is closed on the GPU pool this was developed on (profiles/r02_sanitizer.txt).
+#ifdef SPB_BOUNDS_CHECK
+#define SPB_ASSERT(err, cond, code) do { if (!(cond)) atomicOr((err), (uint32_t)ERRBIT_BOUNDS | ((uint32_t)(code) << 8)); } while (0)
+#else
+#define SPB_ASSERT(err, cond, code) ((void)0)
+#endif
 
 // leaf_info[slot]: depth[0,8) | pending-eval flag (bit 8)
 constexpr uint32_t LEAF_PENDING = 1u << 8;
@@ -116,7 +126,7 @@ __device__ __forceinline__ NodeRec ld_rec(const NodeRec* p) {
 template <class G, bool COHERENT = false>
 __device__ __forceinline__ void descend(const NodeRec* rec, const PState& root, float c, int lane,
                                         WarpPath& path, uint32_t& leaf, int& depth, PState& st, uint32_t& leaf_info,
-                                        uint32_t* err) {
+                                        uint32_t* err, uint32_t n_nodes = 0xFFFFFFFFu) {
   NodeRec r0 = ld_rec<COHERENT>(rec);
   uint32_t node = 0, Np = r0.N, info = r0.info;
   st = root;
@@ -129,6 +139,7 @@ __device__ __forceinline__ void descend(const NodeRec* rec, const PState& root, 
     ch.N = 0; ch.W = 0.0f; ch.P = 0.0f; ch.info = 0;
     float score = -INFINITY;
     int idx = -1;
+    SPB_ASSERT(err, fc + (uint32_t)nc <= n_nodes && nc <= G::A && depth + 1 < G::MAX_DEPTH, 1);
     if (lane < nc) {
       ch = ld_rec<COHERENT>(rec + fc + lane);                // 16-B vector load, children contiguous
       score = puct_score(c, Np, ch.N, ch.W, ch.P);

@@ -65,3 +65,16 @@ def gather_trajectories(engine, dst: int = 0):
     """Drains this rank's finished trajectories and gathers them to the learner rank."""
     pos, ids = engine.drain_trajectories()
     return gather_records(pos, ids, dst=dst)
+
+
+def comm_init_over_process_group(engine, rank: int | None = None, world: int | None = None):
+    """Joins `engine` to a C-ABI communicator (spb_comm_init) spanning the default torch.distributed process group: rank 0
+    creates the NCCL id (spb_comm_unique_id) and the process group only carries its 128 bytes.  A Rust host distributes the
+    id by its own means."""
+    import torch.distributed as dist
+    from .engine import comm_unique_id
+    rank = dist.get_rank() if rank is None else rank
+    world = dist.get_world_size() if world is None else world
+    box = [comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    engine.comm_init(box[0], rank, world)

@@ -94,6 +94,11 @@ ABI = {
     "spb_game_encode": (C.c_int32, [_vp, _vp, C.c_uint32, _vp]),
     "spb_selfplay_step": (C.c_int32, [_vp, C.c_int32, C.c_float, C.c_uint64, _vp, _u32p]),
     "spb_drain_trajectories": (C.c_int32, [_vp, _vp, C.c_size_t, C.POINTER(C.c_size_t), _vp]),
+    "spb_comm_unique_id": (C.c_int32, [_vp]),
+    "spb_comm_init": (C.c_int32, [_vp, _vp, C.c_int32, C.c_int32]),
+    "spb_comm_destroy": (C.c_int32, [_vp]),
+    "spb_gather_trajectories": (C.c_int32, [_vp, C.c_int32, _vp, C.c_size_t, C.POINTER(C.c_size_t), _vp]),
+    "spb_positions_to_training": (C.c_int32, [C.c_int32, _vp, C.c_size_t, _vp, _vp, _vp]),
     "spb_get_counters": (C.c_int32, [_vp, C.POINTER(Counters)]),
     "spb_reset_counters": (C.c_int32, [_vp]),
     "spb_last_search_timing": (C.c_int32, [_vp, _f32p, _f32p, _u32p]),
@@ -152,6 +157,35 @@ def check_weights(game: int, blob: bytes):
     err = C.create_string_buffer(512)
     rc = L.spb_check_weights(game, C.cast(buf, _vp), len(blob), err, 512)
     return rc, err.value.decode()
+
+
+COMM_ID_BYTES = 128
+
+
+def comm_unique_id() -> bytes:
+    """spb_comm_unique_id: the 128-byte NCCL id rank 0 creates and the host distributes to every rank."""
+    L = load_library()
+    buf = (C.c_uint8 * COMM_ID_BYTES)()
+    rc = L.spb_comm_unique_id(C.cast(buf, _vp))
+    if rc != 0:
+        raise EngineError(rc, L.spb_last_error(None).decode())
+    return bytes(buf)
+
+
+def positions_to_training(game: int, positions: np.ndarray):
+    """spb_positions_to_training (host only): -> (encodings[n,3,R,C], policies[n,A], values[n,1]) f32 — the tensors of
+    learner_concurrent.rs:126-146."""
+    L = load_library()
+    pos = np.ascontiguousarray(positions, dtype=POSITION_DTYPE)
+    n = len(pos)
+    R, Cc = BOARD[game]
+    enc = np.zeros((n, 3, R, Cc), np.float32)
+    pol = np.zeros((n, NUM_ACTIONS[game]), np.float32)
+    val = np.zeros((n, 1), np.float32)
+    rc = L.spb_positions_to_training(game, pos.ctypes.data, n, enc.ctypes.data, pol.ctypes.data, val.ctypes.data)
+    if rc != 0:
+        raise EngineError(rc, "spb_positions_to_training: bad argument")
+    return enc, pol, val
 
 
 class Engine:
@@ -306,6 +340,24 @@ class Engine:
         if n.value:
             self._chk(self._L.spb_drain_trajectories(self._h, pos.ctypes.data, n.value, C.byref(n), ids.ctypes.data))
         return pos[:n.value], ids[:n.value]
+
+    # ---- multi-GPU: trajectories to the learner rank --------------------------------------------
+    def comm_init(self, comm_id: bytes, rank: int, world_size: int):
+        buf = (C.c_uint8 * COMM_ID_BYTES).from_buffer_copy(comm_id)
+        self._chk(self._L.spb_comm_init(self._h, C.cast(buf, _vp), rank, world_size))
+
+    def comm_destroy(self):
+        self._chk(self._L.spb_comm_destroy(self._h))
+
+    def gather_trajectories(self, learner_rank: int = 0):
+        """COLLECTIVE: -> (positions, game_ids) ordered by (game id, ply) on the learner rank, empty elsewhere."""
+        n = C.c_size_t()
+        self._chk(self._L.spb_gather_trajectories(self._h, learner_rank, None, 0, C.byref(n), None))
+        pos = np.zeros(n.value, dtype=POSITION_DTYPE)
+        ids = np.zeros(n.value, dtype=np.uint64)
+        if n.value:
+            self._chk(self._L.spb_gather_trajectories(self._h, learner_rank, pos.ctypes.data, n.value, C.byref(n), ids.ctypes.data))
+        return pos, ids
 
     # ---- counters ----------------------------------------------------------------------------
     def counters(self) -> dict:

@@ -107,3 +107,33 @@ def test_flag_and_code_constants_agree_across_header_python_and_rust():
     rust = open(os.path.join(root, "rust", "selfplay-b200-sys", "src", "lib.rs")).read()
     for m in re.finditer(r"pub const (SPB_[A-Z0-9_]+): [iu]32 = (-?\d+);", rust):
         assert defs[m.group(1)] == int(m.group(2)), m.group(1)
+
+
+def test_positions_to_training_matches_the_oracle_encodings():
+    """spb_positions_to_training (host only): the learner's tensors (learner_concurrent.rs:126-146) from compact records —
+    encodings equal the oracle's get_encoding of the recorded state, policies are counts / sum in f32, values the outcome."""
+    from helpers import random_states
+    from oracle import pyoracle as O
+    rng = np.random.default_rng(5)
+    for game in (S.GAME_C4, S.GAME_TTT):
+        A = S.NUM_ACTIONS[game]
+        states = random_states(game, 200, seed=3, include_terminal=False)
+        pos = np.zeros(len(states), dtype=S.POSITION_DTYPE)
+        for i, s in enumerate(states):
+            pos[i]["stones"] = (s.stones[0], s.stones[1])
+            pos[i]["current_player"] = s.current_player
+            pos[i]["ply"] = s.num_actions_played
+            legal = O.valid_actions(game, s)
+            counts = np.zeros(9, np.uint32)
+            counts[legal] = rng.integers(0, 800, len(legal))
+            counts[legal[0]] += 1                                     # at least one visit
+            pos[i]["visit_counts"] = counts
+            pos[i]["outcome"] = int(rng.integers(-1, 2))
+        enc, pol, val = S.positions_to_training(game, pos)
+        assert enc.shape == (len(states), 3) + S.engine.BOARD[game] and pol.shape == (len(states), A) and val.shape == (len(states), 1)
+        for i, s in enumerate(states):
+            assert np.array_equal(enc[i], O.encode(game, s))
+            c = pos[i]["visit_counts"][:A].astype(np.float32)
+            assert np.array_equal(pol[i], c / np.float32(c.sum(dtype=np.float32)))
+            assert val[i, 0] == float(pos[i]["outcome"])
+    assert S.load_library().spb_positions_to_training(7, None, 0, None, None, None) == -1

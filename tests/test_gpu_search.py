@@ -310,3 +310,32 @@ def test_trajectory_buffer_overflow_parks_games_and_loses_nothing():
     got, e1 = play(20)                                            # room for two or three games per ply
     assert e0 == 0 and e1 > 0
     assert len(want) > G * 5 and got == want
+
+
+def _play_generation(e, roots, plies, sims):
+    e.reset_games(roots)
+    for _ in range(plies):
+        e.search(sims)
+        e.selfplay_step(S.MOVE_GREEDY_LAST_MAX, restart_roots=roots)
+
+
+def test_gather_over_the_c_abi_with_one_rank_equals_drain():
+    """spb_gather_trajectories on a one-rank NCCL communicator returns exactly what spb_drain_trajectories returns
+    (ordered by game id, then ply), the size query keeps the records staged, and the learner hand-off tensors follow."""
+    G, plies, sims = 48, 14, 40
+    roots = synthetic_roots(S.GAME_C4, G, start=0)
+    with S.Engine(game=S.GAME_C4, num_games=G, evaluator=S.EVAL_DET) as e:
+        _play_generation(e, roots, plies, sims)
+        want_pos, want_ids = e.drain_trajectories()
+    assert len(want_pos) > 50
+    with S.Engine(game=S.GAME_C4, num_games=G, evaluator=S.EVAL_DET) as e:
+        e.comm_init(S.comm_unique_id(), 0, 1)
+        _play_generation(e, roots, plies, sims)
+        pos, ids = e.gather_trajectories(0)
+        assert pos.tobytes() == want_pos.tobytes() and ids.tobytes() == want_ids.tobytes()
+        again, _ = e.gather_trajectories(0)                      # handed over: nothing left, the local buffer is empty too
+        assert len(again) == 0 and len(e.drain_trajectories()[0]) == 0
+        e.comm_destroy()
+    enc, pol, val = S.positions_to_training(S.GAME_C4, pos)
+    assert enc.shape == (len(pos), 3, 6, 7) and np.allclose(pol.sum(1), 1.0) and set(np.unique(val)) <= {-1.0, 0.0, 1.0}
+    assert np.array_equal(enc[:, 2], 1.0 - enc[:, 0] - enc[:, 1])
