@@ -256,6 +256,61 @@ int32_t spb_selfplay_step(spb_engine* e, int32_t rule, float temperature, uint64
 int32_t spb_drain_trajectories(spb_engine* e, spb_position* buf, size_t capacity, size_t* written,
                                uint64_t* game_ids /* nullable, [capacity] global game id per position */);
 
+/* ---- chess rules, batched on the device (ref: src/game/chess.rs; BASELINE config 5, first half: rules, no search yet) ---- */
+
+#define SPB_CHESS_MAX_MOVES    256    /* capacity of a legal-move list (218 is the known maximum) */
+#define SPB_CHESS_MAX_HISTORY  512    /* plies of game history a state may carry (repetition rule, chess.rs:51-62) */
+#define SPB_CHESS_PLANES       19     /* get_encoding, chess.rs:176-249 */
+#define SPB_CHESS_POLICY_SIZE  4672   /* 73 move planes x 8 x 8, chess.rs:311-493 */
+#define SPB_CHESS_NO_SQUARE    64
+
+/*
+ * A chess position.  Replaces `State{game, transposition_table, fifty_move_rule_halfmove_counter}` (chess.rs:24-29):
+ * bitboards with square = rank*8 + file (a1 = 0, h8 = 63, as Square::to_index of the `chess` crate); the game history the
+ * repetition rule needs travels beside the state as one 64-bit hash per ply (history[i] = hash of the legal-move list of
+ * the position before ply i; the reference compares those lists, chess.rs:51-62,121-122).
+ * A move is uint16: from | to << 6 | promotion << 12 (0 none, 1 knight, 2 bishop, 3 rook, 4 queen).
+ */
+typedef struct spb_chess_state {
+  uint64_t piece[6];             /* pawns, knights, bishops, rooks, queens, kings (both colours) */
+  uint64_t color[2];             /* white, black */
+  uint8_t  side;                 /* side to move: 0 white, 1 black */
+  uint8_t  castle;               /* bit 0 white king side, 1 white queen side, 2 black king side, 3 black queen side */
+  uint8_t  ep;                   /* en-passant target square or SPB_CHESS_NO_SQUARE */
+  uint8_t  reserved0;
+  uint16_t fifty;                /* fifty_move_rule_halfmove_counter (chess.rs:124-143) */
+  uint16_t plies;                /* moves played in the game (get_encoding plane 18) */
+  uint32_t hist_len;             /* plies of history that travel with this state (<= SPB_CHESS_MAX_HISTORY) */
+  uint32_t reserved1;
+} spb_chess_state;               /* 80 bytes */
+
+/* State::default(), chess.rs:94-102 (host only). */
+int32_t spb_chess_start_position(spb_chess_state* out);
+/*
+ * get_valid_actions (chess.rs:150-152) + get_status (:154-166) for n states in one kernel.  history is [n][SPB_CHESS_MAX_HISTORY]
+ * (nullable when every hist_len is 0).  Outputs (each nullable): moves[n][SPB_CHESS_MAX_MOVES] sorted by (from, to, promotion) —
+ * the crate's own order is unknown here: parity unpinned, DESIGN.md §2 —, counts[n], policy_index[n][SPB_CHESS_MAX_MOVES] = position
+ * of each move in the flat 73x8x8 policy (Policy::get_prob, chess.rs:495-502), status[n] (SPB_STATUS_*; Won = the side to
+ * move is checkmated, value +1.0 by chess.rs:172), repetitions[n] (get_num_repetitions, chess.rs:51-62).
+ */
+int32_t spb_chess_legal_moves(spb_engine* e, const spb_chess_state* states, const uint64_t* history, uint32_t n, uint16_t* moves,
+                              uint32_t* counts, uint16_t* policy_index, uint8_t* status, uint32_t* repetitions);
+/*
+ * get_next_state (chess.rs:112-148).  err[i] = SPB_OK, or SPB_ERR_ILLEGAL (move not legal / game already over: the state
+ * is copied unchanged), or SPB_ERR_STATE (history full).  history (nullable only if no state moves) is updated in place:
+ * the hash of the legal-move list of states[i] is appended and out_states[i].hist_len = hist_len + 1.
+ */
+int32_t spb_chess_next_states(spb_engine* e, const spb_chess_state* states, uint64_t* history, const uint16_t* moves, uint32_t n,
+                              spb_chess_state* out_states, int32_t* err);
+/* get_encoding (chess.rs:176-249): out[n][19][8][8] f32. */
+int32_t spb_chess_encode(spb_engine* e, const spb_chess_state* states, const uint64_t* history, uint32_t n, float* out);
+/* perft(depth) of one position on the device (the standard move-generator test): leaf count of the legal-move tree. */
+int32_t spb_chess_perft(spb_engine* e, const spb_chess_state* state, uint32_t depth, uint64_t* nodes);
+/* Policy::get_channel (chess.rs:311-390), the flat policy index, Policy::get_action (:392-493, 0xFFFF = off the board): host only. */
+int32_t spb_chess_move_channel(int32_t side, uint16_t move);
+int32_t spb_chess_policy_index(int32_t side, uint16_t move);
+uint16_t spb_chess_action(int32_t side, int32_t channel, int32_t row, int32_t col);
+
 /* ---- multi-GPU: trajectories to the learner rank; learner hand-off ------- */
 
 /*

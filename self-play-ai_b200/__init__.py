@@ -10,3 +10,5 @@ from .engine import (  # noqa: F401
     Engine, EngineError, Position, check_weights, comm_unique_id, positions_to_training, COMM_ID_BYTES, State, STATE_DTYPE, POSITION_DTYPE, library_path, load_library, build_library,
 )
 from .mcts import Args, Mcts, Tree  # noqa: F401
+from . import chess  # noqa: F401
+from .chess import ChessRules, CHESS_STATE_DTYPE  # noqa: F401

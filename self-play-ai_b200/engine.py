@@ -99,6 +99,15 @@ ABI = {
     "spb_comm_destroy": (C.c_int32, [_vp]),
     "spb_gather_trajectories": (C.c_int32, [_vp, C.c_int32, _vp, C.c_size_t, C.POINTER(C.c_size_t), _vp]),
     "spb_positions_to_training": (C.c_int32, [C.c_int32, _vp, C.c_size_t, _vp, _vp, _vp]),
+    # chess (ref: src/game/chess.rs); typed wrappers in chess.py
+    "spb_chess_start_position": (C.c_int32, [_vp]),
+    "spb_chess_legal_moves": (C.c_int32, [_vp, _vp, _vp, C.c_uint32, _vp, _vp, _vp, _vp, _vp]),
+    "spb_chess_next_states": (C.c_int32, [_vp, _vp, _vp, _vp, C.c_uint32, _vp, _vp]),
+    "spb_chess_encode": (C.c_int32, [_vp, _vp, _vp, C.c_uint32, _vp]),
+    "spb_chess_perft": (C.c_int32, [_vp, _vp, C.c_uint32, C.POINTER(C.c_uint64)]),
+    "spb_chess_move_channel": (C.c_int32, [C.c_int32, C.c_uint16]),
+    "spb_chess_policy_index": (C.c_int32, [C.c_int32, C.c_uint16]),
+    "spb_chess_action": (C.c_uint16, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "spb_get_counters": (C.c_int32, [_vp, C.POINTER(Counters)]),
     "spb_reset_counters": (C.c_int32, [_vp]),
     "spb_last_search_timing": (C.c_int32, [_vp, _f32p, _f32p, _u32p]),
