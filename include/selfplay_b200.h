@@ -256,13 +256,22 @@ int32_t spb_selfplay_step(spb_engine* e, int32_t rule, float temperature, uint64
 int32_t spb_drain_trajectories(spb_engine* e, spb_position* buf, size_t capacity, size_t* written,
                                uint64_t* game_ids /* nullable, [capacity] global game id per position */);
 
-/* ---- chess rules, batched on the device (ref: src/game/chess.rs; BASELINE config 5, first half: rules, no search yet) ---- */
-
+/* ---- chess (ref: src/game/chess.rs, src/model/chess.rs; BASELINE config 5) ------------------------------------------ */
+/*
+ * The chess engine is a handle type of its own: `Mcts<chess Net>` + its `Vec<Tree<chess::State>>` on one GPU.  It is
+ * created from the same spb_config with game = SPB_GAME_CHESS (leaves_per_tree must be 1; max_nodes_per_tree 0 = 32,768).
+ * Everything the reference computes itself is reproduced exactly; what it delegates to the un-vendored crate `chess 3.2.0`
+ * — the ORDER of the legal moves, hence of a node's children — is defined here as sorted by (from, to, promotion):
+ * PARITY UNPINNED for that order; the legal-move SETS are pinned by the published perft counts.
+ */
+#define SPB_GAME_CHESS         2
 #define SPB_CHESS_MAX_MOVES    256    /* capacity of a legal-move list (218 is the known maximum) */
 #define SPB_CHESS_MAX_HISTORY  512    /* plies of game history a state may carry (repetition rule, chess.rs:51-62) */
 #define SPB_CHESS_PLANES       19     /* get_encoding, chess.rs:176-249 */
 #define SPB_CHESS_POLICY_SIZE  4672   /* 73 move planes x 8 x 8, chess.rs:311-493 */
 #define SPB_CHESS_NO_SQUARE    64
+
+typedef struct spb_chess_engine spb_chess_engine;
 
 /*
  * A chess position.  Replaces `State{game, transposition_table, fifty_move_rule_halfmove_counter}` (chess.rs:24-29):
@@ -284,32 +293,69 @@ typedef struct spb_chess_state {
   uint32_t reserved1;
 } spb_chess_state;               /* 80 bytes */
 
+/* lifecycle (ref: Mcts{args, model} construction, main.rs:43-44); errors as for spb_create, text via spb_chess_last_error(NULL) */
+int32_t spb_chess_create(const spb_config* cfg, spb_chess_engine** out);
+int32_t spb_chess_destroy(spb_chess_engine* e);
+const char* spb_chess_last_error(const spb_chess_engine* e);
+/* VarStore::load (main.rs:61) for model/chess.rs:50-73: safetensors bytes, BatchNorm folded, bf16 packed for tcgen05. */
+int32_t spb_chess_load_weights(spb_chess_engine* e, const void* blob, size_t n);
+int32_t spb_chess_check_weights(const void* blob, size_t n, char* err, size_t err_cap);   /* host only */
+
 /* State::default(), chess.rs:94-102 (host only). */
 int32_t spb_chess_start_position(spb_chess_state* out);
 /*
  * get_valid_actions (chess.rs:150-152) + get_status (:154-166) for n states in one kernel.  history is [n][SPB_CHESS_MAX_HISTORY]
- * (nullable when every hist_len is 0).  Outputs (each nullable): moves[n][SPB_CHESS_MAX_MOVES] sorted by (from, to, promotion) —
- * the crate's own order is unknown here: parity unpinned, DESIGN.md §2 —, counts[n], policy_index[n][SPB_CHESS_MAX_MOVES] = position
- * of each move in the flat 73x8x8 policy (Policy::get_prob, chess.rs:495-502), status[n] (SPB_STATUS_*; Won = the side to
- * move is checkmated, value +1.0 by chess.rs:172), repetitions[n] (get_num_repetitions, chess.rs:51-62).
+ * (nullable when every hist_len is 0).  Outputs (each nullable): moves[n][SPB_CHESS_MAX_MOVES] sorted by (from, to, promotion),
+ * counts[n], policy_index[n][SPB_CHESS_MAX_MOVES] = position of each move in the flat 73x8x8 policy (Policy::get_prob,
+ * chess.rs:495-502), status[n] (SPB_STATUS_*; Won = the side to move is checkmated, value +1.0 by chess.rs:172),
+ * repetitions[n] (get_num_repetitions, chess.rs:51-62).
  */
-int32_t spb_chess_legal_moves(spb_engine* e, const spb_chess_state* states, const uint64_t* history, uint32_t n, uint16_t* moves,
+int32_t spb_chess_legal_moves(spb_chess_engine* e, const spb_chess_state* states, const uint64_t* history, uint32_t n, uint16_t* moves,
                               uint32_t* counts, uint16_t* policy_index, uint8_t* status, uint32_t* repetitions);
 /*
  * get_next_state (chess.rs:112-148).  err[i] = SPB_OK, or SPB_ERR_ILLEGAL (move not legal / game already over: the state
  * is copied unchanged), or SPB_ERR_STATE (history full).  history (nullable only if no state moves) is updated in place:
  * the hash of the legal-move list of states[i] is appended and out_states[i].hist_len = hist_len + 1.
  */
-int32_t spb_chess_next_states(spb_engine* e, const spb_chess_state* states, uint64_t* history, const uint16_t* moves, uint32_t n,
+int32_t spb_chess_next_states(spb_chess_engine* e, const spb_chess_state* states, uint64_t* history, const uint16_t* moves, uint32_t n,
                               spb_chess_state* out_states, int32_t* err);
 /* get_encoding (chess.rs:176-249): out[n][19][8][8] f32. */
-int32_t spb_chess_encode(spb_engine* e, const spb_chess_state* states, const uint64_t* history, uint32_t n, float* out);
+int32_t spb_chess_encode(spb_chess_engine* e, const spb_chess_state* states, const uint64_t* history, uint32_t n, float* out);
 /* perft(depth) of one position on the device (the standard move-generator test): leaf count of the legal-move tree. */
-int32_t spb_chess_perft(spb_engine* e, const spb_chess_state* state, uint32_t depth, uint64_t* nodes);
+int32_t spb_chess_perft(spb_chess_engine* e, const spb_chess_state* state, uint32_t depth, uint64_t* nodes);
 /* Policy::get_channel (chess.rs:311-390), the flat policy index, Policy::get_action (:392-493, 0xFFFF = off the board): host only. */
 int32_t spb_chess_move_channel(int32_t side, uint16_t move);
 int32_t spb_chess_policy_index(int32_t side, uint16_t move);
 uint16_t spb_chess_action(int32_t side, int32_t channel, int32_t row, int32_t col);
+
+/* Tree::with_root_state (mcts.rs:86-89) for n slots (slots NULL = 0..n-1; roots NULL = the start position; history
+ * [n][SPB_CHESS_MAX_HISTORY], NULL = games that start at their root). */
+int32_t spb_chess_reset_games(spb_chess_engine* e, const uint32_t* slots, uint32_t n, const spb_chess_state* roots, const uint64_t* history);
+/* Mcts::search (mcts.rs:196-332): num_searches simulations for every live tree.  SPB_EVAL_NET runs the reference's loop
+ * literally — per simulation one select over all trees, one network batch, one expand + backup. */
+int32_t spb_chess_search(spb_chess_engine* e, uint32_t num_searches);
+int32_t spb_chess_last_search_ms(spb_chess_engine* e, float* ms);   /* device time of the last spb_chess_search */
+/* Result of search for one tree / all trees (mcts.rs:315-328), child order: moves, visit counts, arena ids; arrays of
+ * SPB_CHESS_MAX_MOVES entries per tree. */
+int32_t spb_chess_root_children(spb_chess_engine* e, uint32_t slot, uint16_t* moves, uint32_t* visit_counts, uint32_t* child_ids, uint32_t* n_children);
+int32_t spb_chess_root_children_all(spb_chess_engine* e, uint16_t* moves, uint32_t* visit_counts, uint32_t* child_ids, uint32_t* n_children);
+/* The Policy half of the result: visit counts scattered by set_prob and normalised, out[SPB_CHESS_POLICY_SIZE]. */
+int32_t spb_chess_root_policy(spb_chess_engine* e, uint32_t slot, float* out);
+/* Tree::use_subtree(child id) (mcts.rs:161-192) for n trees; the root position advances, the game history grows by one
+ * ply.  out_states (nullable) receives the new root states.  SPB_ERR_ARG if an id is not a child of its root. */
+int32_t spb_chess_advance(spb_chess_engine* e, const uint32_t* slots, const uint32_t* child_ids, uint32_t n, spb_chess_state* out_states);
+/* arena[node_id].state (mcts.rs:22). */
+int32_t spb_chess_get_state(spb_chess_engine* e, uint32_t slot, uint32_t node_id, spb_chess_state* out);
+int32_t spb_chess_arena_len(spb_chess_engine* e, uint32_t slot, uint32_t* out);
+/* Node fields (mcts.rs:20-30); status = SPB_STATUS_* (Ongoing until the node has been reached as a leaf). */
+int32_t spb_chess_node_stats(spb_chess_engine* e, uint32_t slot, uint32_t node_id, uint32_t* visit_count, float* value_sum, float* prior,
+                             uint32_t* first_child, uint32_t* n_children, uint16_t* move, uint8_t* status);
+/* Model::predict (model/mod.rs:36-98): policies[n][4672] = softmax masked to the legal moves and renormalised
+ * (chess.rs:251-271), values[n], raw_logits[n][4672] (each nullable).  n <= num_games. */
+int32_t spb_chess_predict(spb_chess_engine* e, const spb_chess_state* states, const uint64_t* history, uint32_t n, float* policies, float* values,
+                          float* raw_logits);
+int32_t spb_chess_get_counters(spb_chess_engine* e, spb_counters* out);   /* reserved[0] = largest arena */
+int32_t spb_chess_reset_counters(spb_chess_engine* e);
 
 /* ---- multi-GPU: trajectories to the learner rank; learner hand-off ------- */
 

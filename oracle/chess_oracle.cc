@@ -15,6 +15,7 @@
  * (from, to, promotion) — the order this repo defines in place of the crate's.
  */
 #include <algorithm>
+#include <cmath>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
@@ -423,5 +424,247 @@ void orc_chess_export(const orc_chess* c, spb_chess_state* out, uint64_t* histor
   if (history)
     for (size_t i = 0; i < c->g.table.size() && i < SPB_CHESS_MAX_HISTORY; ++i) history[i] = list_hash(c->g.table[i]);
 }
+
+}  // extern "C"
+
+// =====================================================================================================================
+// MCTS over chess states: src/mcts.rs restated for chess.rs's State (the small games have theirs in oracle.cc)
+// =====================================================================================================================
+namespace {
+
+// ndarray 0.15.6 `sum()` on a contiguous f32 array (numeric_util::unrolled_fold), as in oracle.cc; call site chess.rs:268
+float ndarray_sum(const float* xs, size_t n) {
+  float acc = 0.0f;
+  float p[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  while (n >= 8) {
+    for (int i = 0; i < 8; ++i) p[i] = p[i] + xs[i];
+    xs += 8;
+    n -= 8;
+  }
+  acc = acc + (p[0] + p[4]);
+  acc = acc + (p[1] + p[5]);
+  acc = acc + (p[2] + p[6]);
+  acc = acc + (p[3] + p[7]);
+  for (size_t i = 0; i < n && i < 7; ++i) acc = acc + xs[i];
+  return acc;
+}
+
+constexpr int POLICY = SPB_CHESS_POLICY_SIZE;
+
+// Policy::get_prob / set_prob index, chess.rs:495-514
+int policy_index(int player, Move m) {
+  const int from = m & 63;
+  int row = from / 8;
+  if (player == 1) row = 7 - row;
+  return orc_chess_channel(player, m) * 64 + row * 8 + from % 8;
+}
+
+// DetEval for chess (definition shared with csrc/chess_tree.cuh): h = fold of mix64 over the bitboards and the
+// side / castle / en-passant word; raw p(cell) = (1 + 3 bits of mix64(h ^ (2^32 + cell))) / 64; v on the 1/128 grid.
+uint64_t det_hash(const Board& b) {
+  uint64_t piece[6] = {0, 0, 0, 0, 0, 0}, color[2] = {0, 0};
+  for (int s = 0; s < 64; ++s) {
+    if (b.sq[s] == EMPTY) continue;
+    piece[type_of(b.sq[s])] |= 1ull << s;
+    color[color_of(b.sq[s])] |= 1ull << s;
+  }
+  uint64_t h = 0;
+  for (int i = 0; i < 6; ++i) h = mix64(h ^ piece[i]);
+  h = mix64(h ^ color[0]);
+  h = mix64(h ^ color[1]);
+  return mix64(h ^ ((uint64_t)b.side | ((uint64_t)b.castle << 8) | ((uint64_t)b.ep << 16)));
+}
+
+struct MNode {                         // mcts.rs:20-30
+  Game state;
+  long parent_id = -1;
+  Move action_taken = 0xFFFF;
+  float prior = 0.0f;
+  std::vector<size_t> children_ids;
+  uint32_t visit_count = 0;
+  float value_sum = 0.0f;
+  bool is_fully_expanded() const { return !children_ids.empty(); }
+};
+
+struct MTree {                         // mcts.rs:32-39
+  std::vector<MNode> arena;
+  float c = 2.0f;
+
+  float get_ucb(size_t parent_id, size_t child_id) const {            // mcts.rs:91-100
+    const MNode& parent = arena[parent_id];
+    const MNode& child = arena[child_id];
+    float q = 0.0f;
+    if (child.visit_count != 0) q = (-child.value_sum / (float)child.visit_count + 1.0f) / 2.0f;
+    return q + c * child.prior * std::sqrt((float)parent.visit_count) / (1.0f + (float)child.visit_count);
+  }
+  size_t select(size_t parent_id) const {                             // mcts.rs:102-114: Iterator::max_by keeps the LAST maximum
+    const MNode& parent = arena[parent_id];
+    size_t best = parent.children_ids[0];
+    float best_s = get_ucb(parent_id, best);
+    for (size_t i = 1; i < parent.children_ids.size(); ++i) {
+      const float s = get_ucb(parent_id, parent.children_ids[i]);
+      if (!(s < best_s)) { best = parent.children_ids[i]; best_s = s; }
+    }
+    return best;
+  }
+  void expand(size_t parent_id, const std::vector<float>& policy, uint64_t* children_created) {   // mcts.rs:116-143
+    const Game parent_state = arena[parent_id].state;
+    const std::vector<Move> actions = legal_moves(parent_state.b);    // get_valid_actions
+    const size_t first = arena.size();
+    for (size_t i = 0; i < actions.size(); ++i) arena[parent_id].children_ids.push_back(first + i);
+    for (Move a : actions) {
+      MNode ch;
+      ch.state = parent_state;                                        // get_next_state, chess.rs:112-148
+      ch.state.table.push_back(actions);
+      ch.state.b = apply(parent_state.b, a);
+      ch.parent_id = (long)parent_id;
+      ch.action_taken = a;
+      ch.prior = policy[policy_index(parent_state.b.side, a)];        // policy.get_prob(&action)
+      arena.push_back(ch);
+    }
+    *children_created += actions.size();
+  }
+  void backprop(size_t node_id, float value) {                        // mcts.rs:145-159
+    float sign = 1.0f;
+    long id = (long)node_id;
+    while (id >= 0) {
+      arena[id].visit_count += 1;
+      arena[id].value_sum += sign * value;
+      sign *= -1.0f;
+      id = arena[id].parent_id;
+    }
+  }
+  void use_subtree(size_t new_root_id) {                              // mcts.rs:161-192
+    std::vector<MNode> fresh;
+    std::vector<size_t> queue_old{new_root_id};
+    std::vector<long> queue_parent{-1};
+    for (size_t head = 0; head < queue_old.size(); ++head) {
+      MNode node = arena[queue_old[head]];
+      const size_t id = fresh.size();
+      node.parent_id = queue_parent[head];
+      for (size_t child : node.children_ids) { queue_old.push_back(child); queue_parent.push_back((long)id); }
+      node.children_ids.clear();
+      if (node.parent_id >= 0) fresh[node.parent_id].children_ids.push_back(id);
+      fresh.push_back(node);
+    }
+    arena.swap(fresh);
+  }
+};
+
+}  // namespace
+
+extern "C" {
+
+typedef void (*orc_chess_eval_fn)(void* user, const float* encodings, uint32_t n, float* probs, float* values);
+
+struct orc_chess_forest {
+  std::vector<MTree> trees;
+  uint64_t simulations = 0, evaluations = 0, terminal_leaves = 0, path_length_sum = 0, children_created = 0;
+};
+
+orc_chess_forest* orc_chess_forest_new(uint32_t n, float c) {
+  orc_chess_forest* f = new orc_chess_forest();
+  f->trees.resize(n);
+  for (auto& t : f->trees) t.c = c;
+  return f;
+}
+void orc_chess_forest_free(orc_chess_forest* f) { delete f; }
+
+// Tree::with_root_state (mcts.rs:86-89)
+void orc_chess_forest_reset(orc_chess_forest* f, uint32_t slot, const orc_chess* root) {
+  MTree& t = f->trees[slot];
+  t.arena.clear();
+  MNode r;
+  r.state = root->g;
+  t.arena.push_back(r);
+}
+
+// Mcts::search (mcts.rs:196-332).  evaluator: SPB_EVAL_DET / SPB_EVAL_UNIFORM built in, SPB_EVAL_NET via fn (softmax
+// output of the net over the 4,672 cells, NOT masked; the oracle applies mask_invalid_actions, chess.rs:251-271).
+void orc_chess_forest_search(orc_chess_forest* f, uint32_t num_searches, int32_t evaluator, orc_chess_eval_fn fn, void* user) {
+  for (uint32_t it = 0; it < num_searches; ++it) {                                 // :214
+    std::vector<MTree*> to_expand;
+    std::vector<size_t> node_ids;
+    for (MTree& tree : f->trees) {                                                 // :236
+      if (tree.arena.empty()) continue;
+      size_t node = 0;
+      while (tree.arena[node].is_fully_expanded()) { node = tree.select(node); f->path_length_sum++; }   // :239
+      const int st = status(tree.arena[node].state);                               // get_value_and_terminated :243
+      f->simulations++;
+      if (st != SPB_STATUS_ONGOING) {
+        tree.backprop(node, st == SPB_STATUS_WON ? 1.0f : 0.0f);                   // :246, chess.rs:172
+        f->terminal_leaves++;
+      } else {
+        to_expand.push_back(&tree);
+        node_ids.push_back(node);
+      }
+    }
+    if (to_expand.empty()) continue;
+    const size_t n = to_expand.size();
+    std::vector<float> probs(n * POLICY), values(n, 0.0f);
+    if (evaluator == SPB_EVAL_DET) {
+      for (size_t i = 0; i < n; ++i) {
+        const uint64_t h = det_hash(to_expand[i]->arena[node_ids[i]].state.b);
+        for (int k = 0; k < POLICY; ++k) probs[i * POLICY + k] = (float)(1u + (uint32_t)(mix64(h ^ (0x100000000ull + (uint64_t)k)) & 7u)) * (1.0f / 64.0f);
+        values[i] = ((float)((h >> 40) & 0xFFu) - 128.0f) * (1.0f / 128.0f);
+      }
+    } else if (evaluator == SPB_EVAL_UNIFORM) {
+      for (auto& p : probs) p = 1.0f;
+    } else {
+      std::vector<float> enc(n * 19 * 64);
+      for (size_t i = 0; i < n; ++i) {
+        orc_chess tmp;
+        tmp.g = to_expand[i]->arena[node_ids[i]].state;
+        orc_chess_encode(&tmp, &enc[i * 19 * 64]);                                  // model/mod.rs:41-44
+      }
+      fn(user, enc.data(), (uint32_t)n, probs.data(), values.data());              // :60-67, :95
+    }
+    f->evaluations += n;
+    for (size_t i = 0; i < n; ++i) {                                               // :278-284
+      MTree* tree = to_expand[i];
+      const Game& st = tree->arena[node_ids[i]].state;
+      // mask_invalid_actions, chess.rs:251-271: probs * mask, divided by the ndarray sum of the masked array
+      std::vector<float> masked(POLICY, 0.0f);
+      for (Move m : legal_moves(st.b)) { const int k = policy_index(st.b.side, m); masked[k] = probs[i * POLICY + k] * 1.0f; }
+      const float sum = ndarray_sum(masked.data(), POLICY);
+      for (auto& x : masked) x = x / sum;
+      tree->expand(node_ids[i], masked, &f->children_created);
+      tree->backprop(node_ids[i], values[i]);
+    }
+  }
+}
+
+int32_t orc_chess_forest_root_children(const orc_chess_forest* f, uint32_t slot, uint16_t* moves, uint32_t* counts, uint32_t* ids) {
+  const MTree& t = f->trees[slot];
+  const auto& ch = t.arena[0].children_ids;
+  for (size_t i = 0; i < ch.size(); ++i) {
+    if (moves) moves[i] = t.arena[ch[i]].action_taken;
+    if (counts) counts[i] = t.arena[ch[i]].visit_count;
+    if (ids) ids[i] = (uint32_t)ch[i];
+  }
+  return (int32_t)ch.size();
+}
+uint32_t orc_chess_forest_arena_len(const orc_chess_forest* f, uint32_t slot) { return (uint32_t)f->trees[slot].arena.size(); }
+int32_t orc_chess_forest_node(const orc_chess_forest* f, uint32_t slot, uint32_t id, uint32_t* n, float* w, float* p, uint32_t* first_child,
+                              uint32_t* n_children, uint16_t* move) {
+  const MTree& t = f->trees[slot];
+  if (id >= t.arena.size()) return SPB_ERR_ARG;
+  const MNode& nd = t.arena[id];
+  *n = nd.visit_count; *w = nd.value_sum; *p = nd.prior;
+  *first_child = nd.children_ids.empty() ? 0u : (uint32_t)nd.children_ids[0];
+  *n_children = (uint32_t)nd.children_ids.size();
+  *move = nd.action_taken;
+  return SPB_OK;
+}
+void orc_chess_forest_use_subtree(orc_chess_forest* f, uint32_t slot, uint32_t id) { f->trees[slot].use_subtree(id); }
+orc_chess* orc_chess_forest_state(const orc_chess_forest* f, uint32_t slot, uint32_t id) {
+  orc_chess* c = new orc_chess();
+  c->g = f->trees[slot].arena[id].state;
+  return c;
+}
+void orc_chess_forest_counters(const orc_chess_forest* f, uint64_t* out) {
+  out[0] = f->simulations; out[1] = f->evaluations; out[2] = f->terminal_leaves; out[3] = f->path_length_sum; out[4] = f->children_created;
+}
+uint64_t orc_chess_det_hash(const orc_chess* c) { return det_hash(c->g.b); }
 
 }  // extern "C"

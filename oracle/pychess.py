@@ -35,6 +35,7 @@ CHESS_STATE_DTYPE = np.dtype([("piece", "<u8", (6,)), ("color", "<u8", (2,)), ("
                               ("reserved0", "u1"), ("fifty", "<u2"), ("plies", "<u2"), ("hist_len", "<u4"), ("reserved1", "<u4")])
 assert CHESS_STATE_DTYPE.itemsize == C.sizeof(ChessState) == 80
 
+CHESS_EVAL_FN = C.CFUNCTYPE(None, C.c_void_p, C.POINTER(C.c_float), C.c_uint32, C.POINTER(C.c_float), C.POINTER(C.c_float))
 _bound = False
 
 
@@ -57,6 +58,19 @@ def _lib():
         L.orc_chess_channel.restype, L.orc_chess_channel.argtypes = C.c_int32, [C.c_int32, C.c_uint16]
         L.orc_chess_action.restype, L.orc_chess_action.argtypes = C.c_uint16, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]
         L.orc_chess_export.argtypes = [vp, C.POINTER(ChessState), C.POINTER(C.c_uint64)]
+        L.orc_chess_det_hash.restype, L.orc_chess_det_hash.argtypes = C.c_uint64, [vp]
+        u32p = C.POINTER(C.c_uint32)
+        L.orc_chess_forest_new.restype, L.orc_chess_forest_new.argtypes = vp, [C.c_uint32, C.c_float]
+        L.orc_chess_forest_free.argtypes = [vp]
+        L.orc_chess_forest_reset.argtypes = [vp, C.c_uint32, vp]
+        L.orc_chess_forest_search.argtypes = [vp, C.c_uint32, C.c_int32, CHESS_EVAL_FN, vp]
+        L.orc_chess_forest_root_children.restype, L.orc_chess_forest_root_children.argtypes = C.c_int32, [vp, C.c_uint32, u16p, u32p, u32p]
+        L.orc_chess_forest_arena_len.restype, L.orc_chess_forest_arena_len.argtypes = C.c_uint32, [vp, C.c_uint32]
+        L.orc_chess_forest_node.restype = C.c_int32
+        L.orc_chess_forest_node.argtypes = [vp, C.c_uint32, C.c_uint32, u32p, f32p, f32p, u32p, u32p, u16p]
+        L.orc_chess_forest_use_subtree.argtypes = [vp, C.c_uint32, C.c_uint32]
+        L.orc_chess_forest_state.restype, L.orc_chess_forest_state.argtypes = vp, [vp, C.c_uint32, C.c_uint32]
+        L.orc_chess_forest_counters.argtypes = [vp, C.POINTER(C.c_uint64)]
         _bound = True
     return L
 
@@ -111,6 +125,66 @@ class Game:
         hist = np.zeros(MAX_HISTORY, np.uint64)
         _lib().orc_chess_export(self._h, C.byref(s), hist.ctypes.data_as(C.POINTER(C.c_uint64)))
         return s, hist
+
+
+class Forest:
+    """`Mcts::search` over chess trees (src/mcts.rs restated in oracle/chess_oracle.cc)."""
+
+    def __init__(self, n: int, c: float = 2.0):
+        self._h = _lib().orc_chess_forest_new(n, c)
+        self.n = n
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            _lib().orc_chess_forest_free(self._h)
+            self._h = None
+
+    def reset(self, slot: int, game: "Game"):
+        _lib().orc_chess_forest_reset(self._h, slot, game._h)
+
+    def search(self, num_searches: int, evaluator: int, net_fn=None):
+        """evaluator: 1 DetEval, 2 uniform, 0 network via net_fn(encodings[n,19,8,8]) -> (softmax probs[n,4672], values[n])."""
+        if net_fn is None:
+            cb = CHESS_EVAL_FN()
+        else:
+            def _cb(user, enc, n, probs, values):
+                e = np.ctypeslib.as_array(enc, shape=(n, PLANES, 8, 8))
+                p, v = net_fn(e)
+                np.ctypeslib.as_array(probs, shape=(n, POLICY_SIZE))[:] = p
+                np.ctypeslib.as_array(values, shape=(n,))[:] = v
+            cb = CHESS_EVAL_FN(_cb)
+        _lib().orc_chess_forest_search(self._h, num_searches, evaluator, cb, None)
+
+    def root_children(self, slot: int):
+        mv, cnt, ids = (C.c_uint16 * MAX_MOVES)(), (C.c_uint32 * MAX_MOVES)(), (C.c_uint32 * MAX_MOVES)()
+        n = _lib().orc_chess_forest_root_children(self._h, slot, mv, cnt, ids)
+        return list(mv[:n]), list(cnt[:n]), list(ids[:n])
+
+    def arena_len(self, slot: int) -> int:
+        return _lib().orc_chess_forest_arena_len(self._h, slot)
+
+    def node(self, slot: int, node_id: int) -> dict:
+        n, fc, nc = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        w, p = C.c_float(), C.c_float()
+        mv = C.c_uint16()
+        rc = _lib().orc_chess_forest_node(self._h, slot, node_id, C.byref(n), C.byref(w), C.byref(p), C.byref(fc), C.byref(nc), C.byref(mv))
+        assert rc == 0
+        return dict(visit_count=n.value, value_sum=w.value, prior=p.value, first_child=fc.value, n_children=nc.value, move=mv.value)
+
+    def use_subtree(self, slot: int, node_id: int):
+        _lib().orc_chess_forest_use_subtree(self._h, slot, node_id)
+
+    def state(self, slot: int, node_id: int) -> "Game":
+        return Game(_h=_lib().orc_chess_forest_state(self._h, slot, node_id))
+
+    def counters(self) -> dict:
+        v = (C.c_uint64 * 5)()
+        _lib().orc_chess_forest_counters(self._h, v)
+        return dict(zip(("simulations", "evaluations", "terminal_leaves", "path_length_sum", "children_created"), (int(x) for x in v)))
+
+
+def det_hash(game: "Game") -> int:
+    return int(_lib().orc_chess_det_hash(game._h))
 
 
 def channel(player: int, move: int) -> int:

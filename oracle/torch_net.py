@@ -169,3 +169,90 @@ def load_tch_safetensors(blob: bytes, game: int):
         fill_conv(net.pconv); fill_bn(net.pbn); fill_conv(net.pfc)
         fill_conv(net.vconv); fill_bn(net.vbn); fill_conv(net.vfc)
     return net
+
+
+# ---- chess (ref: src/model/chess.rs:50-83) ---------------------------------------------------------------------------
+
+class ChessNet(nn.Module):
+    """19 -> 256 stem, 10 residual blocks, policy head conv1x1 256 -> 256, ReLU, conv1x1 256 -> 73 (flat 73*8*8), value head
+    conv1x1 256 -> 1, ReLU, Linear 64 -> 256, ReLU, Linear 256 -> 1, tanh."""
+
+    def __init__(self, blocks=10, hidden=256):
+        super().__init__()
+        self.stem = nn.Conv2d(19, hidden, 3, padding=1)
+        self.stem_bn = nn.BatchNorm2d(hidden)
+        self.blocks = nn.ModuleList([ResBlock(hidden) for _ in range(blocks)])
+        self.p1 = nn.Conv2d(hidden, 256, 1)
+        self.p2 = nn.Conv2d(256, 73, 1)
+        self.vconv = nn.Conv2d(hidden, 1, 1)
+        self.fc1 = nn.Linear(64, 256)
+        self.fc2 = nn.Linear(256, 1)
+
+    def forward(self, x):
+        x = x.view(-1, 19, 8, 8)
+        x = torch.relu(self.stem_bn(self.stem(x)))
+        for b in self.blocks:
+            x = b(x)
+        p = self.p2(torch.relu(self.p1(x))).flatten(1)
+        v = torch.tanh(self.fc2(torch.relu(self.fc1(torch.relu(self.vconv(x)).flatten(1)))))
+        return p, v
+
+    def conv_bn_pairs(self):
+        pairs = [(self.stem, self.stem_bn)]
+        for b in self.blocks:
+            pairs += [(b.conv1, b.bn1), (b.conv2, b.bn2)]
+        return pairs
+
+
+def make_chess_net(seed=0, randomize_bn=True, blocks=10):
+    g = torch.Generator().manual_seed(seed)
+    torch.manual_seed(seed)
+    net = ChessNet(blocks=blocks).eval()
+    if randomize_bn:
+        with torch.no_grad():
+            for _, bn in net.conv_bn_pairs():
+                bn.running_mean.copy_(torch.randn(bn.num_features, generator=g) * 0.1)
+                bn.running_var.copy_(torch.rand(bn.num_features, generator=g) * 0.5 + 0.75)
+                bn.weight.copy_(torch.rand(bn.num_features, generator=g) * 0.5 + 0.75)
+                bn.bias.copy_(torch.randn(bn.num_features, generator=g) * 0.1)
+    return net
+
+
+def chess_to_safetensors_explicit(net) -> bytes:
+    out = []
+    for i, (conv, bn) in enumerate(net.conv_bn_pairs()):
+        out += [("conv%d.weight" % i, conv.weight), ("conv%d.bias" % i, conv.bias), ("bn%d.weight" % i, bn.weight),
+                ("bn%d.bias" % i, bn.bias), ("bn%d.running_mean" % i, bn.running_mean), ("bn%d.running_var" % i, bn.running_var)]
+    for name, m in (("policy_conv1", net.p1), ("policy_conv2", net.p2), ("value_conv", net.vconv), ("value_fc1", net.fc1), ("value_fc2", net.fc2)):
+        out += [(name + ".weight", m.weight), (name + ".bias", m.bias)]
+    return _write_safetensors([(n, t.detach().numpy()) for n, t in out])
+
+
+def chess_to_safetensors_tch(net, shuffle_seed=None) -> bytes:
+    """tch VarStore names with every layer on the root path (model/chess.rs:55-71): creation order torso, policy head, value head."""
+    created = []
+    def wb(m):
+        created.extend([("bias", m.bias), ("weight", m.weight)])
+    for c, b in net.conv_bn_pairs():
+        wb(c)
+        for k in ("weight", "bias", "running_mean", "running_var"):
+            created.append((k, getattr(b, k)))
+    for m in (net.p1, net.p2, net.vconv, net.fc1, net.fc2):
+        wb(m)
+    named, seen = [], set()
+    for base, t in created:
+        name = base if base not in seen else "%s__%d" % (base, len(named))
+        seen.add(base)
+        named.append((name, t.detach().numpy()))
+    if shuffle_seed is not None:
+        rng = np.random.default_rng(shuffle_seed)
+        named = [named[i] for i in rng.permutation(len(named))]
+    return _write_safetensors(named)
+
+
+def chess_forward(net, enc):
+    """-> (softmax over the 4,672 cells, values, raw logits)."""
+    with torch.no_grad():
+        x = torch.from_numpy(np.ascontiguousarray(enc, dtype=np.float32))
+        p, v = net(x)
+        return torch.softmax(p, -1).numpy(), v.reshape(-1).numpy(), p.numpy()

@@ -2,8 +2,7 @@
 // Rules: chess.cuh (bitboards, __host__ __device__); reference: src/game/chess.rs.  BASELINE config 5, first half: the
 // State / Policy interface of the chess adapter as device kernels, validated by perft and an array-board oracle.  The
 // chess search (trees over these rules, the 10x256 net of src/model/chess.rs) is the next step, see DESIGN.md §7.
-#include "chess.cuh"
-#include "engine.hpp"
+#include "chess_engine.hpp"
 
 namespace spb {
 namespace chess {
@@ -126,23 +125,7 @@ __global__ void k_frontier_expand(const Pos* frontier, uint32_t n, const uint32_
 using namespace spb;
 namespace ch = spb::chess;
 
-#define CH_GUARD(e)                                                   \
-  if (!(e)) return SPB_ERR_ARG;                                       \
-  if (cudaSetDevice((e)->cfg.device) != cudaSuccess) { (e)->set_error("cudaSetDevice failed"); return SPB_ERR_CUDA; }
-
-namespace {
-// device scratch for one call: a few plain allocations (these entry points are test / tooling paths, not the hot path)
-struct Scratch {
-  std::vector<void*> ptrs;
-  ~Scratch() { for (void* p : ptrs) cudaFree(p); }
-  template <class T> T* alloc(size_t count) {
-    void* p = nullptr;
-    if (cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T)) != cudaSuccess) return nullptr;
-    ptrs.push_back(p);
-    return static_cast<T*>(p);
-  }
-};
-}  // namespace
+using spb::chess::Scratch;
 
 extern "C" {
 
@@ -158,7 +141,7 @@ uint16_t spb_chess_action(int32_t side, int32_t channel, int32_t row, int32_t co
   return ch::action(side & 1, channel, row, col);
 }
 
-int32_t spb_chess_legal_moves(spb_engine* e, const spb_chess_state* states, const uint64_t* history, uint32_t n, uint16_t* moves,
+int32_t spb_chess_legal_moves(spb_chess_engine* e, const spb_chess_state* states, const uint64_t* history, uint32_t n, uint16_t* moves,
                               uint32_t* counts, uint16_t* policy_index, uint8_t* status, uint32_t* repetitions) {
   CH_GUARD(e);
   if (n == 0) return SPB_OK;
@@ -175,23 +158,23 @@ int32_t spb_chess_legal_moves(spb_engine* e, const spb_chess_state* states, cons
     e->set_error("chess: out of device memory");
     return SPB_ERR_NOMEM;
   }
-  SPB_CUDA_E(e, cudaMemcpyAsync(d_states, states, (size_t)n * sizeof(ch::Pos), cudaMemcpyHostToDevice, e->stream));
-  if (history) SPB_CUDA_E(e, cudaMemcpyAsync(d_hist, history, (size_t)n * SPB_CHESS_MAX_HISTORY * 8, cudaMemcpyHostToDevice, e->stream));
-  if (d_moves) SPB_CUDA_E(e, cudaMemsetAsync(d_moves, 0xFF, (size_t)n * SPB_CHESS_MAX_MOVES * 2, e->stream));
-  if (d_pidx) SPB_CUDA_E(e, cudaMemsetAsync(d_pidx, 0xFF, (size_t)n * SPB_CHESS_MAX_MOVES * 2, e->stream));
+  CH_CUDA(e, cudaMemcpyAsync(d_states, states, (size_t)n * sizeof(ch::Pos), cudaMemcpyHostToDevice, e->stream));
+  if (history) CH_CUDA(e, cudaMemcpyAsync(d_hist, history, (size_t)n * SPB_CHESS_MAX_HISTORY * 8, cudaMemcpyHostToDevice, e->stream));
+  if (d_moves) CH_CUDA(e, cudaMemsetAsync(d_moves, 0xFF, (size_t)n * SPB_CHESS_MAX_MOVES * 2, e->stream));
+  if (d_pidx) CH_CUDA(e, cudaMemsetAsync(d_pidx, 0xFF, (size_t)n * SPB_CHESS_MAX_MOVES * 2, e->stream));
   ch::k_legal<<<(n + 63) / 64, 64, 0, e->stream>>>(d_states, d_hist, n, d_moves, d_counts, d_pidx, d_status, d_reps);
-  SPB_CUDA_E(e, cudaGetLastError());
+  CH_CUDA(e, cudaGetLastError());
   ++e->launches;
-  if (moves) SPB_CUDA_E(e, cudaMemcpyAsync(moves, d_moves, (size_t)n * SPB_CHESS_MAX_MOVES * 2, cudaMemcpyDeviceToHost, e->stream));
-  if (policy_index) SPB_CUDA_E(e, cudaMemcpyAsync(policy_index, d_pidx, (size_t)n * SPB_CHESS_MAX_MOVES * 2, cudaMemcpyDeviceToHost, e->stream));
-  if (counts) SPB_CUDA_E(e, cudaMemcpyAsync(counts, d_counts, (size_t)n * 4, cudaMemcpyDeviceToHost, e->stream));
-  if (repetitions) SPB_CUDA_E(e, cudaMemcpyAsync(repetitions, d_reps, (size_t)n * 4, cudaMemcpyDeviceToHost, e->stream));
-  if (status) SPB_CUDA_E(e, cudaMemcpyAsync(status, d_status, (size_t)n, cudaMemcpyDeviceToHost, e->stream));
-  SPB_CUDA_E(e, cudaStreamSynchronize(e->stream));
+  if (moves) CH_CUDA(e, cudaMemcpyAsync(moves, d_moves, (size_t)n * SPB_CHESS_MAX_MOVES * 2, cudaMemcpyDeviceToHost, e->stream));
+  if (policy_index) CH_CUDA(e, cudaMemcpyAsync(policy_index, d_pidx, (size_t)n * SPB_CHESS_MAX_MOVES * 2, cudaMemcpyDeviceToHost, e->stream));
+  if (counts) CH_CUDA(e, cudaMemcpyAsync(counts, d_counts, (size_t)n * 4, cudaMemcpyDeviceToHost, e->stream));
+  if (repetitions) CH_CUDA(e, cudaMemcpyAsync(repetitions, d_reps, (size_t)n * 4, cudaMemcpyDeviceToHost, e->stream));
+  if (status) CH_CUDA(e, cudaMemcpyAsync(status, d_status, (size_t)n, cudaMemcpyDeviceToHost, e->stream));
+  CH_CUDA(e, cudaStreamSynchronize(e->stream));
   return SPB_OK;
 }
 
-int32_t spb_chess_next_states(spb_engine* e, const spb_chess_state* states, uint64_t* history, const uint16_t* moves, uint32_t n,
+int32_t spb_chess_next_states(spb_chess_engine* e, const spb_chess_state* states, uint64_t* history, const uint16_t* moves, uint32_t n,
                               spb_chess_state* out_states, int32_t* err) {
   CH_GUARD(e);
   if (n == 0) return SPB_OK;
@@ -203,20 +186,20 @@ int32_t spb_chess_next_states(spb_engine* e, const spb_chess_state* states, uint
   auto* d_moves = sc.alloc<uint16_t>(n);
   auto* d_err = sc.alloc<int32_t>(n);
   if (!d_states || !d_out || (history && !d_hist) || !d_moves || !d_err) { e->set_error("chess: out of device memory"); return SPB_ERR_NOMEM; }
-  SPB_CUDA_E(e, cudaMemcpyAsync(d_states, states, (size_t)n * sizeof(ch::Pos), cudaMemcpyHostToDevice, e->stream));
-  SPB_CUDA_E(e, cudaMemcpyAsync(d_moves, moves, (size_t)n * 2, cudaMemcpyHostToDevice, e->stream));
-  if (history) SPB_CUDA_E(e, cudaMemcpyAsync(d_hist, history, (size_t)n * SPB_CHESS_MAX_HISTORY * 8, cudaMemcpyHostToDevice, e->stream));
+  CH_CUDA(e, cudaMemcpyAsync(d_states, states, (size_t)n * sizeof(ch::Pos), cudaMemcpyHostToDevice, e->stream));
+  CH_CUDA(e, cudaMemcpyAsync(d_moves, moves, (size_t)n * 2, cudaMemcpyHostToDevice, e->stream));
+  if (history) CH_CUDA(e, cudaMemcpyAsync(d_hist, history, (size_t)n * SPB_CHESS_MAX_HISTORY * 8, cudaMemcpyHostToDevice, e->stream));
   ch::k_next<<<(n + 63) / 64, 64, 0, e->stream>>>(d_states, d_hist, d_moves, n, d_out, d_err);
-  SPB_CUDA_E(e, cudaGetLastError());
+  CH_CUDA(e, cudaGetLastError());
   ++e->launches;
-  SPB_CUDA_E(e, cudaMemcpyAsync(out_states, d_out, (size_t)n * sizeof(ch::Pos), cudaMemcpyDeviceToHost, e->stream));
-  SPB_CUDA_E(e, cudaMemcpyAsync(err, d_err, (size_t)n * 4, cudaMemcpyDeviceToHost, e->stream));
-  if (history) SPB_CUDA_E(e, cudaMemcpyAsync(history, d_hist, (size_t)n * SPB_CHESS_MAX_HISTORY * 8, cudaMemcpyDeviceToHost, e->stream));
-  SPB_CUDA_E(e, cudaStreamSynchronize(e->stream));
+  CH_CUDA(e, cudaMemcpyAsync(out_states, d_out, (size_t)n * sizeof(ch::Pos), cudaMemcpyDeviceToHost, e->stream));
+  CH_CUDA(e, cudaMemcpyAsync(err, d_err, (size_t)n * 4, cudaMemcpyDeviceToHost, e->stream));
+  if (history) CH_CUDA(e, cudaMemcpyAsync(history, d_hist, (size_t)n * SPB_CHESS_MAX_HISTORY * 8, cudaMemcpyDeviceToHost, e->stream));
+  CH_CUDA(e, cudaStreamSynchronize(e->stream));
   return SPB_OK;
 }
 
-int32_t spb_chess_encode(spb_engine* e, const spb_chess_state* states, const uint64_t* history, uint32_t n, float* out) {
+int32_t spb_chess_encode(spb_chess_engine* e, const spb_chess_state* states, const uint64_t* history, uint32_t n, float* out) {
   CH_GUARD(e);
   if (n == 0) return SPB_OK;
   if (!states || !out) { e->set_error("null argument"); return SPB_ERR_ARG; }
@@ -225,17 +208,17 @@ int32_t spb_chess_encode(spb_engine* e, const spb_chess_state* states, const uin
   auto* d_hist = history ? sc.alloc<uint64_t>((size_t)n * SPB_CHESS_MAX_HISTORY) : nullptr;
   auto* d_out = sc.alloc<float>((size_t)n * SPB_CHESS_PLANES * 64);
   if (!d_states || (history && !d_hist) || !d_out) { e->set_error("chess: out of device memory"); return SPB_ERR_NOMEM; }
-  SPB_CUDA_E(e, cudaMemcpyAsync(d_states, states, (size_t)n * sizeof(ch::Pos), cudaMemcpyHostToDevice, e->stream));
-  if (history) SPB_CUDA_E(e, cudaMemcpyAsync(d_hist, history, (size_t)n * SPB_CHESS_MAX_HISTORY * 8, cudaMemcpyHostToDevice, e->stream));
+  CH_CUDA(e, cudaMemcpyAsync(d_states, states, (size_t)n * sizeof(ch::Pos), cudaMemcpyHostToDevice, e->stream));
+  if (history) CH_CUDA(e, cudaMemcpyAsync(d_hist, history, (size_t)n * SPB_CHESS_MAX_HISTORY * 8, cudaMemcpyHostToDevice, e->stream));
   ch::k_encode<<<n, 128, 0, e->stream>>>(d_states, d_hist, n, d_out);
-  SPB_CUDA_E(e, cudaGetLastError());
+  CH_CUDA(e, cudaGetLastError());
   ++e->launches;
-  SPB_CUDA_E(e, cudaMemcpyAsync(out, d_out, (size_t)n * SPB_CHESS_PLANES * 64 * 4, cudaMemcpyDeviceToHost, e->stream));
-  SPB_CUDA_E(e, cudaStreamSynchronize(e->stream));
+  CH_CUDA(e, cudaMemcpyAsync(out, d_out, (size_t)n * SPB_CHESS_PLANES * 64 * 4, cudaMemcpyDeviceToHost, e->stream));
+  CH_CUDA(e, cudaStreamSynchronize(e->stream));
   return SPB_OK;
 }
 
-int32_t spb_chess_perft(spb_engine* e, const spb_chess_state* state, uint32_t depth, uint64_t* nodes) {
+int32_t spb_chess_perft(spb_chess_engine* e, const spb_chess_state* state, uint32_t depth, uint64_t* nodes) {
   CH_GUARD(e);
   if (!state || !nodes) { e->set_error("null argument"); return SPB_ERR_ARG; }
   if (depth > 8) { e->set_error("perft depth > 8"); return SPB_ERR_ARG; }
@@ -247,18 +230,18 @@ int32_t spb_chess_perft(spb_engine* e, const spb_chess_state* state, uint32_t de
   ch::Pos* d_f = nullptr;
   if (cudaMalloc(&d_f, sizeof(ch::Pos)) != cudaSuccess || !d_total) { e->set_error("chess: out of device memory"); return SPB_ERR_NOMEM; }
   struct Free { ch::Pos*& p; ~Free() { cudaFree(p); } } free_f{d_f};
-  SPB_CUDA_E(e, cudaMemcpyAsync(d_f, state, sizeof(ch::Pos), cudaMemcpyHostToDevice, e->stream));
+  CH_CUDA(e, cudaMemcpyAsync(d_f, state, sizeof(ch::Pos), cudaMemcpyHostToDevice, e->stream));
   uint32_t n = 1, remaining = depth;
   while (remaining > 0 && (n < 4096 || remaining > (uint32_t)ch::PERFT_DEV_DEPTH)) {
     uint32_t* d_off = nullptr;
     if (cudaMalloc(&d_off, (size_t)n * 4) != cudaSuccess) { e->set_error("chess: out of device memory"); return SPB_ERR_NOMEM; }
     struct FreeOff { uint32_t* p; ~FreeOff() { cudaFree(p); } } free_off{d_off};
-    SPB_CUDA_E(e, cudaMemsetAsync(d_total, 0, 8, e->stream));
+    CH_CUDA(e, cudaMemsetAsync(d_total, 0, 8, e->stream));
     ch::k_frontier_count<<<(n + 63) / 64, 64, 0, e->stream>>>(d_f, n, d_off, d_total);
-    SPB_CUDA_E(e, cudaGetLastError());
+    CH_CUDA(e, cudaGetLastError());
     unsigned long long m = 0;
-    SPB_CUDA_E(e, cudaMemcpyAsync(&m, d_total, 8, cudaMemcpyDeviceToHost, e->stream));
-    SPB_CUDA_E(e, cudaStreamSynchronize(e->stream));
+    CH_CUDA(e, cudaMemcpyAsync(&m, d_total, 8, cudaMemcpyDeviceToHost, e->stream));
+    CH_CUDA(e, cudaStreamSynchronize(e->stream));
     e->launches += 1;
     if (m == 0) { *nodes = 0; return SPB_OK; }
     if (m > (1ull << 23)) { e->set_error("perft frontier too large"); return SPB_ERR_ARG; }
@@ -269,18 +252,18 @@ int32_t spb_chess_perft(spb_engine* e, const spb_chess_state* state, uint32_t de
     cudaStreamSynchronize(e->stream);
     cudaFree(d_f);
     d_f = d_next;
-    SPB_CUDA_E(e, err);
+    CH_CUDA(e, err);
     e->launches += 1;
     n = (uint32_t)m;
     --remaining;
   }
-  SPB_CUDA_E(e, cudaMemsetAsync(d_total, 0, 8, e->stream));
+  CH_CUDA(e, cudaMemsetAsync(d_total, 0, 8, e->stream));
   ch::k_perft<<<(n + 63) / 64, 64, 0, e->stream>>>(d_f, n, (int)remaining, d_total);
-  SPB_CUDA_E(e, cudaGetLastError());
+  CH_CUDA(e, cudaGetLastError());
   ++e->launches;
   unsigned long long total = 0;
-  SPB_CUDA_E(e, cudaMemcpyAsync(&total, d_total, 8, cudaMemcpyDeviceToHost, e->stream));
-  SPB_CUDA_E(e, cudaStreamSynchronize(e->stream));
+  CH_CUDA(e, cudaMemcpyAsync(&total, d_total, 8, cudaMemcpyDeviceToHost, e->stream));
+  CH_CUDA(e, cudaStreamSynchronize(e->stream));
   *nodes = total;
   return SPB_OK;
 }

@@ -1,0 +1,612 @@
+// chess_net.cu — the chess policy/value network on tcgen05 tensor cores (sm_100a).
+//
+// Replaces Net::forward of src/model/chess.rs:75-83 (torso src/model/mod.rs:152-184) and the tensor part of Model::predict
+// (src/model/mod.rs:60-67).  Unlike the 4 x 64 nets (evaluator_umma.cu), a batch of chess activations does not fit in shared
+// memory (256 channels x 64 cells x 2 B = 32 KB per position), so the network runs layer by layer over the whole leaf
+// batch: one launch of k_conv per convolution, activations in HBM/L2 between layers (bf16), all arithmetic f32-accumulated.
+//
+// Activation layout ("planar, 81-row boards"): a position is 9 x 9 = 81 rows (8 x 8 cells + one zero pad column + one
+// zero pad row, the pad row shared with the next position), so a 3x3 tap (dy,dx) is the constant row offset dy*9+dx and
+// the pads supply the conv's zero padding.  Channels are split into chunks of 8 (16 bytes); HBM holds one plane per
+// chunk, [chunk][row][8 ch] — a tile of rows of one chunk is one contiguous run (one cp.async.bulk) and lands in shared
+// memory as the K-major no-swizzle UMMA operand layout (8-row core matrices of 128 contiguous bytes at ANY row offset, so a
+// tap shift is just the descriptor's start address: verified by tools/umma_probe.cu).
+//
+// k_conv<KC32, TAPS, N, EPI>: persistent CTAs, one 128-row M tile at a time, implicit GEMM M = 128, N = 256 (80 for the last
+// policy conv), K = TAPS x KC32 x 32:
+//   warp 0      producer: A tile (128 + 2 x 16 halo rows, all input channels, loaded ONCE and reused by the 9 taps; double
+//               buffered) and the weight stream (16 KB stages of 32 input channels x 256 outputs through a 4-deep ring),
+//               cp.async.bulk + mbarrier complete_tx
+//   warp 1      MMA issuer: tcgen05.mma.cta_group::1.kind::f16 M = 128, N = 256, K = 16: 128 cycles each = the tensor
+//               pipe's rate, 144 per tile; accumulators in TMEM, 2 x 256 columns (double buffered)
+//   warps 2-5   epilogue: tcgen05.ld -> + bias (+ skip) -> ReLU -> bf16 -> HBM (pad rows forced to zero), or f32 logits
+// The epilogue of tile i and the A load of tile i+2 overlap the MMAs of tile i+1.
+// Algorithmic bytes per tile-layer: A 80 KB + weights 1,152 KB (L2-resident, 1.2 MB per layer) in, 64 KB out, against
+// 151 MFLOP: the kernel is tensor-bound (18.4 k cycles of MMA per tile) if L2 sustains 64 B/clk/SM of weight traffic.
+#include <cuda_bf16.h>
+
+#include <cstring>
+
+#include "chess_engine.hpp"
+#include "chess_net.cuh"
+#include "umma_ptx.cuh"
+
+namespace spb {
+namespace chess {
+
+using namespace spb::umma;
+
+constexpr int BOARD_ROWS = 81;        // rows of one position
+constexpr int LEAD = 16;              // zero rows in front of the first position (taps reach back 10 rows)
+constexpr int QA = 160;               // rows of an A tile in shared memory: 16 halo + 128 + 16 halo
+constexpr int NSTAGE = 4;             // weight ring depth
+constexpr int CONV_THREADS = 192;
+constexpr int IN_CHUNKS = 4;          // stem input: 19 planes padded to 32 channels
+
+__host__ __device__ constexpr uint32_t tiles_for(uint32_t boards) { return (boards * BOARD_ROWS + 127u) / 128u; }
+__host__ __device__ constexpr size_t plane_rows_for(uint32_t max_boards) { return (size_t)LEAD + (size_t)tiles_for(max_boards) * 128 + 32; }
+
+struct ConvArgs {
+  const uint8_t* in;        // planar bf16 [KC32*4][plane_rows][8]
+  uint8_t* out;             // planar bf16 [N/8][plane_rows][8] (EPI 0 / 1; EPI 1 adds the skip it reads from `out` itself)
+  const uint8_t* w;         // weight stages, [tap][kc32][4 chunks][N][8] bf16
+  const float* bias;        // [N]
+  const uint32_t* count;    // positions in this batch (device)
+  uint32_t plane_rows;
+  float* logits;            // EPI 2: [slot][4672]
+  const uint32_t* list;     // EPI 2: slot of position i (nullptr: identity)
+};
+
+enum { EPI_RELU = 0, EPI_SKIP_RELU = 1, EPI_LOGITS = 2 };
+
+template <int KC32, int TAPS, int N, int EPI>
+struct ConvCfg {
+  static constexpr int A_CHUNKS = KC32 * 4;
+  static constexpr uint32_t A_BYTES = (uint32_t)A_CHUNKS * QA * 16;
+  static constexpr uint32_t STAGE_BYTES = 4u * N * 16;
+  static constexpr uint32_t OFF_B = 2 * A_BYTES;
+  static constexpr uint32_t OFF_BIAS = OFF_B + NSTAGE * STAGE_BYTES;
+  static constexpr uint32_t OFF_BAR = OFF_BIAS + 256 * 4;
+  static constexpr uint32_t SMEM = OFF_BAR + 32 * 8;
+};
+
+template <int KC32, int TAPS, int N, int EPI>
+__global__ void __launch_bounds__(CONV_THREADS, 1) k_conv(const ConvArgs a) {
+  using Cfg = ConvCfg<KC32, TAPS, N, EPI>;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bar0 = sbase + Cfg::OFF_BAR;
+  // barriers: a_full[2] a_empty[2] acc_full[2] acc_empty[2] b_full[NSTAGE] b_empty[NSTAGE], then the TMEM base word
+  const uint32_t A_FULL = bar0, A_EMPTY = bar0 + 16, ACC_FULL = bar0 + 32, ACC_EMPTY = bar0 + 48, B_FULL = bar0 + 64, B_EMPTY = bar0 + 64 + NSTAGE * 8;
+  uint32_t* tmem_word = reinterpret_cast<uint32_t*>(smem + Cfg::OFF_BAR + 30 * 8);
+  float* s_bias = reinterpret_cast<float*>(smem + Cfg::OFF_BIAS);
+
+  const uint32_t boards = *a.count;
+  const uint32_t rows_used = boards * BOARD_ROWS;
+  const uint32_t n_tiles = tiles_for(boards);
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(A_FULL + i * 8, 1); mbar_init(A_EMPTY + i * 8, 1);
+      mbar_init(ACC_FULL + i * 8, 1); mbar_init(ACC_EMPTY + i * 8, 4);
+    }
+    for (int i = 0; i < NSTAGE; ++i) { mbar_init(B_FULL + i * 8, 1); mbar_init(B_EMPTY + i * 8, 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < N; i += CONV_THREADS) s_bias[i] = a.bias[i];
+  if (warp == 1) tmem_alloc(smem_u32(tmem_word), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_word;
+
+  if (warp == 0) {
+    // ---- producer ---------------------------------------------------------------------------------------------
+    if (elect_one()) {
+      auto load_a = [&](uint32_t it, uint32_t tile) {
+        const uint32_t buf = it & 1u;
+        mbar_wait_sleep(A_EMPTY + buf * 8, ((it >> 1) & 1u) ^ 1u);
+        mbar_expect_tx(A_FULL + buf * 8, Cfg::A_BYTES);
+        const uint8_t* src = a.in + (size_t)tile * 128 * 16;      // rows [LEAD + 128 tile - 16, +160)
+#pragma unroll 4
+        for (int c = 0; c < Cfg::A_CHUNKS; ++c)
+          bulk_g2s(sbase + buf * Cfg::A_BYTES + (uint32_t)c * QA * 16, src + (size_t)c * a.plane_rows * 16, QA * 16, A_FULL + buf * 8);
+      };
+      uint32_t it = 0, st = 0;
+      if (blockIdx.x < n_tiles) load_a(0, blockIdx.x);
+      for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        if (tile + gridDim.x < n_tiles) load_a(it + 1, tile + gridDim.x);
+        for (int s = 0; s < TAPS * KC32; ++s, ++st) {
+          const uint32_t slot = st % NSTAGE;
+          mbar_wait_sleep(B_EMPTY + slot * 8, ((st / NSTAGE) & 1u) ^ 1u);
+          mbar_expect_tx(B_FULL + slot * 8, Cfg::STAGE_BYTES);
+          bulk_g2s(sbase + Cfg::OFF_B + slot * Cfg::STAGE_BYTES, a.w + (size_t)s * Cfg::STAGE_BYTES, Cfg::STAGE_BYTES, B_FULL + slot * 8);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---- MMA issuer -------------------------------------------------------------------------------------------
+    const bool issuer = elect_one();
+    constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);          // SBO = 128 B, descriptor version 1
+    constexpr uint32_t IDESC = make_idesc(N);
+    uint32_t it = 0, st = 0;
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const uint32_t buf = it & 1u, par = (it >> 1) & 1u;
+      mbar_wait(A_FULL + buf * 8, par);
+      mbar_wait(ACC_EMPTY + buf * 8, par ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + buf * 256;
+      const uint32_t a_lo_base = (((sbase + buf * Cfg::A_BYTES) >> 4) + 16u) | ((uint32_t)QA << 16);   // row 16 of the buffer, LBO = QA rows
+#pragma unroll 1
+      for (int tap = 0; tap < TAPS; ++tap) {
+        const int shift = TAPS == 9 ? (tap / 3 - 1) * 9 + (tap % 3 - 1) : 0;
+#pragma unroll 1
+        for (int kc = 0; kc < KC32; ++kc, ++st) {
+          const uint32_t slot = st % NSTAGE;
+          mbar_wait(B_FULL + slot * 8, (st / NSTAGE) & 1u);
+          tc_fence_after();
+          if (issuer) {
+            const uint32_t b_lo_base = ((sbase + Cfg::OFF_B + slot * Cfg::STAGE_BYTES) >> 4) | ((uint32_t)N << 16);
+#pragma unroll
+            for (int kk = 0; kk < 2; ++kk) {
+              const uint32_t a_lo = a_lo_base + (uint32_t)(shift + (kc * 4 + kk * 2) * QA);
+              const uint32_t b_lo = b_lo_base + (uint32_t)(kk * 2 * N);
+              umma_f16(d_tmem, ((uint64_t)DESC_HI << 32) | a_lo, ((uint64_t)DESC_HI << 32) | b_lo, IDESC, (tap | kc | kk) != 0);
+            }
+            umma_commit(B_EMPTY + slot * 8);
+          }
+          __syncwarp();
+        }
+      }
+      if (issuer) {
+        umma_commit(ACC_FULL + buf * 8);
+        umma_commit(A_EMPTY + buf * 8);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ---- epilogue ---------------------------------------------------------------------------------------------
+    const int q = warp & 3;                                            // TMEM lane quadrant this warp may read
+    uint32_t it = 0;
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const uint32_t buf = it & 1u, par = (it >> 1) & 1u;
+      mbar_wait(ACC_FULL + buf * 8, par);
+      tc_fence_after();
+      const uint32_t r_global = tile * 128 + (uint32_t)(q * 32 + lane);
+      const uint32_t board = r_global / BOARD_ROWS, cell = r_global % BOARD_ROWS;
+      const bool pad = r_global >= rows_used || cell % 9 == 8 || cell / 9 == 8;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 256;
+      if (EPI == EPI_LOGITS) {
+        const uint32_t slot = (!pad && a.list) ? a.list[board] : board;
+        float* dst = a.logits + (size_t)slot * SPB_CHESS_POLICY_SIZE + (cell / 9) * 8 + (cell % 9);
+#pragma unroll 1
+        for (int c16 = 0; c16 < N / 16; ++c16) {
+          uint32_t r[16];
+          tmem_ld16(taddr + c16 * 16, r);
+          tmem_ld_wait();
+          if (!pad) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int ch = c16 * 16 + j;
+              if (ch < NET_MOVE_PLANES) dst[ch * 64] = __uint_as_float(r[j]) + s_bias[ch];
+            }
+          }
+        }
+      } else {
+        uint8_t* orow = a.out + ((size_t)LEAD + r_global) * 16;
+#pragma unroll 1
+        for (int c32 = 0; c32 < N / 32; ++c32) {
+          uint32_t r[32];
+          tmem_ld16(taddr + c32 * 32, r);
+          tmem_ld16(taddr + c32 * 32 + 16, r + 16);
+          uint4 sk[4];
+          if (EPI == EPI_SKIP_RELU) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) sk[c] = *reinterpret_cast<const uint4*>(orow + (size_t)(c32 * 4 + c) * a.plane_rows * 16);
+          }
+          tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int ch0 = c32 * 32 + c * 8;
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[c * 8 + j]) + s_bias[ch0 + j];
+            if (EPI == EPI_SKIP_RELU) {
+              const uint32_t s4[4] = {sk[c].x, sk[c].y, sk[c].z, sk[c].w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) { v[2 * j] += bf_lo(s4[j]); v[2 * j + 1] += bf_hi(s4[j]); }
+            }
+            uint4 o;
+            o.x = pack_bf16x2(fmaxf(v[0], 0.f), fmaxf(v[1], 0.f));
+            o.y = pack_bf16x2(fmaxf(v[2], 0.f), fmaxf(v[3], 0.f));
+            o.z = pack_bf16x2(fmaxf(v[4], 0.f), fmaxf(v[5], 0.f));
+            o.w = pack_bf16x2(fmaxf(v[6], 0.f), fmaxf(v[7], 0.f));
+            if (pad) o = make_uint4(0u, 0u, 0u, 0u);
+            *reinterpret_cast<uint4*>(orow + (size_t)(c32 * 4 + c) * a.plane_rows * 16) = o;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ACC_EMPTY + buf * 8);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// ---- input planes (get_encoding, chess.rs:176-249) as the stem's A operand: [4 chunks][rows][8] bf16 ------------------
+__global__ void k_encode_input(const Pos* pos, const uint32_t* reps, const uint32_t* list, const uint32_t* count, uint8_t* out, uint32_t plane_rows) {
+  const uint32_t boards = *count;
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;          // row of the batch
+  const uint32_t n_rows = tiles_for(boards) * 128;
+  if (r >= n_rows) return;
+  const uint32_t board = r / BOARD_ROWS, cell = r % BOARD_ROWS, row = cell / 9, col = cell % 9;
+  float v[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = 0.0f;
+  if (board < boards && row < 8 && col < 8) {
+    const uint32_t slot = list ? list[board] : board;
+    const Pos p = pos[slot];
+    const uint32_t rp = reps[slot];
+#pragma unroll
+    for (int pl = 0; pl < NET_IN; ++pl) v[pl] = encode_plane(p, rp, pl, (int)row, (int)col);
+  }
+#pragma unroll
+  for (int c = 0; c < IN_CHUNKS; ++c) {
+    uint4 o;
+    o.x = pack_bf16x2(v[c * 8 + 0], v[c * 8 + 1]);
+    o.y = pack_bf16x2(v[c * 8 + 2], v[c * 8 + 3]);
+    o.z = pack_bf16x2(v[c * 8 + 4], v[c * 8 + 5]);
+    o.w = pack_bf16x2(v[c * 8 + 6], v[c * 8 + 7]);
+    *reinterpret_cast<uint4*>(out + ((size_t)c * plane_rows + LEAD + r) * 16) = o;
+  }
+}
+
+// ---- value head (model/chess.rs:61-70): 1x1 conv 256 -> 1, ReLU, Linear 64 -> 256, ReLU, Linear 256 -> 1, tanh ----------
+// One block of 256 threads per position; f32 weights, bf16 torso output.
+__global__ void __launch_bounds__(256) k_value_head(const uint8_t* x, uint32_t plane_rows, const uint32_t* list, const uint32_t* count,
+                                                    const float* vconv_w, const float* vconv_b, const float* fc1_w, const float* fc1_b,
+                                                    const float* fc2_w, const float* fc2_b, float* values) {
+  __shared__ float s_part[4][64];
+  __shared__ float s_cell[64];
+  __shared__ float s_red[8];
+  const uint32_t board = blockIdx.x;
+  if (board >= *count) return;
+  const int t = threadIdx.x, cell = t & 63, part = t >> 6;             // 4 threads per cell, 8 chunks each
+  const uint32_t r = board * BOARD_ROWS + (cell / 8) * 9 + (cell % 8);
+  float acc = 0.0f;
+  for (int c = part * 8; c < part * 8 + 8; ++c) {
+    const uint4 u = *reinterpret_cast<const uint4*>(x + ((size_t)c * plane_rows + LEAD + r) * 16);
+    const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc += bf_lo(w4[j]) * vconv_w[c * 8 + 2 * j] + bf_hi(w4[j]) * vconv_w[c * 8 + 2 * j + 1];
+  }
+  s_part[part][cell] = acc;
+  __syncthreads();
+  if (t < 64) s_cell[t] = fmaxf(s_part[0][t] + s_part[1][t] + s_part[2][t] + s_part[3][t] + vconv_b[0], 0.0f);
+  __syncthreads();
+  float h = fc1_b[t];
+  for (int k = 0; k < 64; ++k) h += fc1_w[t * 64 + k] * s_cell[k];
+  float y = fmaxf(h, 0.0f) * fc2_w[t];
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) y += __shfl_xor_sync(0xffffffffu, y, o);
+  if ((t & 31) == 0) s_red[t >> 5] = y;
+  __syncthreads();
+  if (t == 0) {
+    float s = fc2_b[0];
+    for (int i = 0; i < 8; ++i) s += s_red[i];
+    values[list ? list[board] : board] = tanhf(s);
+  }
+}
+
+// ---- host ------------------------------------------------------------------------------------------------------------
+struct Net {
+  uint32_t max_positions = 0;
+  size_t plane_rows = 0;
+  uint8_t* d_in = nullptr;      // [4][plane_rows][8] bf16
+  uint8_t* d_x = nullptr;       // [32][plane_rows][8]
+  uint8_t* d_y = nullptr;
+  uint8_t* d_w = nullptr;       // weight image
+  size_t w_bytes = 0;
+  size_t off_conv[NET_CONV3] = {}, off_p1 = 0, off_p2 = 0;
+  float* d_f = nullptr;         // f32 parameters: biases + value head
+  size_t off_bias[NET_CONV3] = {}, off_bp1 = 0, off_bp2 = 0, off_vw = 0, off_vb = 0, off_f1w = 0, off_f1b = 0, off_f2w = 0, off_f2b = 0;
+  bool loaded = false;
+  bool attrs_set = false;
+};
+
+static inline uint16_t f2bf(float f) {
+  uint32_t u;
+  std::memcpy(&u, &f, 4);
+  if ((u & 0x7F800000u) == 0x7F800000u) return (uint16_t)(u >> 16);
+  u += 0x7FFFu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+
+// weight stages of one conv: [tap][kc32][4 chunks][N][8] bf16; input channels padded to kc32*32, outputs to N
+static void pack_conv(const HostNet::Conv& cv, int kc32, int N, uint16_t* dst) {
+  const int taps = cv.k * cv.k;
+  for (int tap = 0; tap < taps; ++tap)
+    for (int kc = 0; kc < kc32; ++kc) {
+      uint16_t* st = dst + ((size_t)tap * kc32 + kc) * 4 * N * 8;
+      for (int n = 0; n < N; ++n)
+        for (int kl = 0; kl < 32; ++kl) {
+          const int k = kc * 32 + kl;
+          const float w = (n < cv.oc && k < cv.ic) ? cv.w[((size_t)n * cv.ic + k) * taps + tap] : 0.0f;
+          st[((size_t)(kl / 8) * N + n) * 8 + (kl % 8)] = f2bf(w);
+        }
+    }
+}
+
+Net* net_create(uint32_t max_positions, std::string* err) {
+  Net* net = new (std::nothrow) Net();
+  if (!net) { *err = "out of host memory"; return nullptr; }
+  net->max_positions = max_positions;
+  net->plane_rows = plane_rows_for(max_positions);
+  const size_t plane = net->plane_rows * 16;
+  size_t w = 0;
+  for (int i = 0; i < NET_CONV3; ++i) { net->off_conv[i] = w; w += (size_t)9 * (i == 0 ? 1 : 8) * 4 * 256 * 16; }
+  net->off_p1 = w; w += (size_t)8 * 4 * 256 * 16;
+  net->off_p2 = w; w += (size_t)8 * 4 * 80 * 16;
+  net->w_bytes = w;
+  size_t f = 0;
+  for (int i = 0; i < NET_CONV3; ++i) { net->off_bias[i] = f; f += 256; }
+  net->off_bp1 = f; f += 256;
+  net->off_bp2 = f; f += 256;
+  net->off_vw = f; f += 256;
+  net->off_vb = f; f += 8;
+  net->off_f1w = f; f += 256 * 64;
+  net->off_f1b = f; f += 256;
+  net->off_f2w = f; f += 256;
+  net->off_f2b = f; f += 8;
+  if (cudaMalloc(&net->d_in, IN_CHUNKS * plane) != cudaSuccess || cudaMalloc(&net->d_x, 32 * plane) != cudaSuccess ||
+      cudaMalloc(&net->d_y, 32 * plane) != cudaSuccess || cudaMalloc(&net->d_w, net->w_bytes) != cudaSuccess ||
+      cudaMalloc(&net->d_f, f * 4) != cudaSuccess) {
+    *err = "out of device memory for the chess network's activations";
+    net_destroy(net);
+    return nullptr;
+  }
+  // lead / tail rows are never written by a kernel: zero once
+  cudaMemset(net->d_in, 0, IN_CHUNKS * plane);
+  cudaMemset(net->d_x, 0, 32 * plane);
+  cudaMemset(net->d_y, 0, 32 * plane);
+  return net;
+}
+
+void net_destroy(Net* net) {
+  if (!net) return;
+  cudaFree(net->d_in); cudaFree(net->d_x); cudaFree(net->d_y); cudaFree(net->d_w); cudaFree(net->d_f);
+  delete net;
+}
+
+bool net_loaded(const Net* net) { return net && net->loaded; }
+
+double net_flops_per_position() {
+  double f = 2.0 * 64 * NET_IN * 9 * 256;                               // stem
+  f += 20.0 * 2.0 * 64 * 256 * 9 * 256;                                 // residual convs
+  f += 2.0 * 64 * 256 * 256 + 2.0 * 64 * 256 * NET_MOVE_PLANES;         // policy head
+  f += 2.0 * 64 * 256 + 2.0 * 64 * 256 + 2.0 * 256;                     // value head
+  return f;
+}
+
+bool net_upload(Net* net, const HostNet& h, std::string* err) {
+  std::vector<uint16_t> img(net->w_bytes / 2, 0);
+  for (int i = 0; i < NET_CONV3; ++i) pack_conv(h.conv3[i], i == 0 ? 1 : 8, 256, img.data() + net->off_conv[i] / 2);
+  pack_conv(h.p1, 8, 256, img.data() + net->off_p1 / 2);
+  pack_conv(h.p2, 8, 80, img.data() + net->off_p2 / 2);
+  std::vector<float> f(net->off_f2b + 8, 0.0f);
+  for (int i = 0; i < NET_CONV3; ++i) std::copy(h.conv3[i].b.begin(), h.conv3[i].b.end(), f.begin() + net->off_bias[i]);
+  std::copy(h.p1.b.begin(), h.p1.b.end(), f.begin() + net->off_bp1);
+  std::copy(h.p2.b.begin(), h.p2.b.end(), f.begin() + net->off_bp2);
+  std::copy(h.vconv.w.begin(), h.vconv.w.end(), f.begin() + net->off_vw);
+  f[net->off_vb] = h.vconv.b[0];
+  std::copy(h.fc1_w.begin(), h.fc1_w.end(), f.begin() + net->off_f1w);
+  std::copy(h.fc1_b.begin(), h.fc1_b.end(), f.begin() + net->off_f1b);
+  std::copy(h.fc2_w.begin(), h.fc2_w.end(), f.begin() + net->off_f2w);
+  f[net->off_f2b] = h.fc2_b[0];
+  if (cudaMemcpy(net->d_w, img.data(), net->w_bytes, cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(net->d_f, f.data(), f.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
+    *err = std::string("weight upload: ") + cudaGetErrorString(cudaGetLastError());
+    return false;
+  }
+  net->loaded = true;
+  return true;
+}
+
+template <int KC32, int TAPS, int N, int EPI>
+static cudaError_t launch_conv(Net* net, const ConvArgs& a, cudaStream_t stream) {
+  using Cfg = ConvCfg<KC32, TAPS, N, EPI>;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(k_conv<KC32, TAPS, N, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+    if (e != cudaSuccess) return e;
+    attr = true;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const uint32_t grid = std::min<uint32_t>((uint32_t)sms, tiles_for(net->max_positions));
+  k_conv<KC32, TAPS, N, EPI><<<grid, CONV_THREADS, Cfg::SMEM, stream>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t net_forward(Net* net, const Pos* pos, const uint32_t* reps, const uint32_t* list, const uint32_t* count_dev, float* logits,
+                        float* values, cudaStream_t stream, uint32_t* launched) {
+  const uint32_t plane_rows = (uint32_t)net->plane_rows;
+  const uint32_t max_rows = tiles_for(net->max_positions) * 128;
+  uint32_t n = 0;
+  cudaError_t e;
+  k_encode_input<<<(max_rows + 127) / 128, 128, 0, stream>>>(pos, reps, list, count_dev, net->d_in, plane_rows);
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  ++n;
+  ConvArgs a{};
+  a.count = count_dev; a.plane_rows = plane_rows; a.list = list; a.logits = logits;
+  // stem: x = relu(bn(conv(in)))
+  a.in = net->d_in; a.out = net->d_x; a.w = net->d_w + net->off_conv[0]; a.bias = net->d_f + net->off_bias[0];
+  if ((e = launch_conv<1, 9, 256, EPI_RELU>(net, a, stream)) != cudaSuccess) return e;
+  ++n;
+  for (int b = 0; b < NET_BLOCKS; ++b) {                               // resnet_block, model/mod.rs:152-166
+    a.in = net->d_x; a.out = net->d_y; a.w = net->d_w + net->off_conv[1 + 2 * b]; a.bias = net->d_f + net->off_bias[1 + 2 * b];
+    if ((e = launch_conv<8, 9, 256, EPI_RELU>(net, a, stream)) != cudaSuccess) return e;
+    a.in = net->d_y; a.out = net->d_x; a.w = net->d_w + net->off_conv[2 + 2 * b]; a.bias = net->d_f + net->off_bias[2 + 2 * b];
+    if ((e = launch_conv<8, 9, 256, EPI_SKIP_RELU>(net, a, stream)) != cudaSuccess) return e;   // x = relu(x + f(x)), in place
+    n += 2;
+  }
+  // policy head: y = relu(conv1x1(x)); logits = conv1x1(y)
+  a.in = net->d_x; a.out = net->d_y; a.w = net->d_w + net->off_p1; a.bias = net->d_f + net->off_bp1;
+  if ((e = launch_conv<8, 1, 256, EPI_RELU>(net, a, stream)) != cudaSuccess) return e;
+  a.in = net->d_y; a.out = nullptr; a.w = net->d_w + net->off_p2; a.bias = net->d_f + net->off_bp2;
+  if ((e = launch_conv<8, 1, 80, EPI_LOGITS>(net, a, stream)) != cudaSuccess) return e;
+  n += 2;
+  k_value_head<<<net->max_positions, 256, 0, stream>>>(net->d_x, plane_rows, list, count_dev, net->d_f + net->off_vw, net->d_f + net->off_vb,
+                                                       net->d_f + net->off_f1w, net->d_f + net->off_f1b, net->d_f + net->off_f2w,
+                                                       net->d_f + net->off_f2b, values);
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  ++n;
+  if (launched) *launched = n;
+  return cudaSuccess;
+}
+
+int32_t net_forward_leaves(spb_chess_engine* e, uint32_t* launched) {
+  const cudaError_t ce = net_forward(e->net, e->T.leaf_pos, e->T.leaf_reps, e->T.eval_list, e->T.eval_count, e->T.eval_logits, e->T.eval_value,
+                                     e->stream, launched);
+  if (ce != cudaSuccess) { e->set_error(std::string("chess network launch: ") + cudaGetErrorString(ce)); return SPB_ERR_CUDA; }
+  return SPB_OK;
+}
+
+// ---- spb_chess_predict: Model::predict (model/mod.rs:36-98) for explicit states -----------------------------------------
+// legal moves, repetition count and status of every state (one warp each), for the encoding's plane 16 and the mask
+__global__ void __launch_bounds__(128) k_predict_prepare(const Pos* states, const unsigned long long* history, uint32_t n, Move* moves,
+                                                         uint32_t* nmoves, uint32_t* reps, uint32_t* error) {
+  __shared__ WarpScratch s_ws[4];
+  const int lane = threadIdx.x & 31;
+  WarpScratch& ws = s_ws[threadIdx.x >> 5];
+  const uint32_t i = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (i >= n) return;
+  const Pos p = states[i];
+  const int m = warp_legal_moves(p, lane, ws, error);
+  const unsigned long long h = warp_list_hash(ws, m, lane);
+  const uint32_t hl = history ? min(p.hist_len, (uint32_t)SPB_CHESS_MAX_HISTORY) : 0u;
+  const uint32_t r = warp_repetitions(h, history + (size_t)i * SPB_CHESS_MAX_HISTORY, hl, ws, 0, lane);
+  for (int k = lane; k < m; k += 32) moves[(size_t)i * MAX_MOVES + k] = ws.moves[k];
+  if (lane == 0) { nmoves[i] = (uint32_t)m; reps[i] = r; }
+}
+
+// softmax over the 4,672 logits (model/mod.rs:64), then mask_invalid_actions (chess.rs:251-271): legal cells / their sum
+__global__ void __launch_bounds__(256) k_predict_mask(const float* logits, const Pos* states, const Move* moves, const uint32_t* nmoves, uint32_t n,
+                                                      float* policies) {
+  __shared__ float s_red[8];
+  __shared__ float s_bcast;
+  const uint32_t i = blockIdx.x;
+  if (i >= n) return;
+  const float* l = logits + (size_t)i * SPB_CHESS_POLICY_SIZE;
+  float* out = policies + (size_t)i * SPB_CHESS_POLICY_SIZE;
+  const int t = threadIdx.x;
+  auto block_reduce = [&](float v, bool is_max) {
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) { const float u = __shfl_xor_sync(0xffffffffu, v, o); v = is_max ? fmaxf(v, u) : v + u; }
+    if ((t & 31) == 0) s_red[t >> 5] = v;
+    __syncthreads();
+    if (t == 0) { float r = s_red[0]; for (int k = 1; k < 8; ++k) r = is_max ? fmaxf(r, s_red[k]) : r + s_red[k]; s_bcast = r; }
+    __syncthreads();
+    const float r = s_bcast;
+    __syncthreads();
+    return r;
+  };
+  float mx = -INFINITY;
+  for (int k = t; k < SPB_CHESS_POLICY_SIZE; k += 256) mx = fmaxf(mx, l[k]);
+  mx = block_reduce(mx, true);
+  float z = 0.0f;
+  for (int k = t; k < SPB_CHESS_POLICY_SIZE; k += 256) { z += __expf(l[k] - mx); out[k] = 0.0f; }
+  z = block_reduce(z, false);
+  __syncthreads();
+  const int side = states[i].side;
+  const uint32_t m = nmoves[i];
+  float s = 0.0f;
+  for (uint32_t k = t; k < m; k += 256) s += __expf(l[policy_index(side, moves[(size_t)i * MAX_MOVES + k])] - mx) / z;
+  s = block_reduce(s, false);
+  for (uint32_t k = t; k < m; k += 256) {
+    const int idx = policy_index(side, moves[(size_t)i * MAX_MOVES + k]);
+    out[idx] = (__expf(l[idx] - mx) / z) / s;
+  }
+}
+
+}  // namespace chess
+}  // namespace spb
+
+namespace ch = spb::chess;
+
+extern "C" {
+
+int32_t spb_chess_load_weights(spb_chess_engine* e, const void* blob, size_t n) {
+  CH_GUARD(e);
+  CH_ARG(e, blob && n > 8, "null / empty weight blob");
+  ch::HostNet host;
+  std::string err;
+  if (!ch::parse_safetensors_chess(blob, n, &host, &err)) { e->set_error("spb_chess_load_weights: " + err); return SPB_ERR_WEIGHTS; }
+  cudaStreamSynchronize(e->stream);
+  if (!e->net) {
+    e->net = ch::net_create(e->T.G, &err);
+    if (!e->net) { e->set_error("spb_chess_load_weights: " + err); return SPB_ERR_NOMEM; }
+  }
+  if (!ch::net_upload(e->net, host, &err)) { e->set_error("spb_chess_load_weights: " + err); return SPB_ERR_CUDA; }
+  return SPB_OK;
+}
+
+int32_t spb_chess_check_weights(const void* blob, size_t n, char* err, size_t err_cap) {
+  if (err && err_cap) err[0] = 0;
+  if (!blob) return SPB_ERR_ARG;
+  ch::HostNet host;
+  std::string msg;
+  if (!ch::parse_safetensors_chess(blob, n, &host, &msg)) {
+    if (err && err_cap) { std::strncpy(err, msg.c_str(), err_cap - 1); err[err_cap - 1] = 0; }
+    return SPB_ERR_WEIGHTS;
+  }
+  return SPB_OK;
+}
+
+int32_t spb_chess_predict(spb_chess_engine* e, const spb_chess_state* states, const uint64_t* history, uint32_t n, float* policies, float* values,
+                          float* raw_logits) {
+  CH_GUARD(e);
+  if (n == 0) return SPB_OK;
+  CH_ARG(e, states, "null states");
+  CH_ARG(e, e->net && ch::net_loaded(e->net), "no weights loaded (spb_chess_load_weights)");
+  CH_ARG(e, n <= e->T.G, "more states than the engine's num_games (the network's batch capacity)");
+  ch::Scratch sc;
+  auto* d_states = sc.alloc<ch::Pos>(n);
+  auto* d_hist = history ? sc.alloc<unsigned long long>((size_t)n * SPB_CHESS_MAX_HISTORY) : nullptr;
+  auto* d_moves = sc.alloc<ch::Move>((size_t)n * ch::MAX_MOVES);
+  auto* d_nmoves = sc.alloc<uint32_t>(n);
+  auto* d_reps = sc.alloc<uint32_t>(n);
+  auto* d_count = sc.alloc<uint32_t>(1);
+  auto* d_logits = sc.alloc<float>((size_t)n * SPB_CHESS_POLICY_SIZE);
+  auto* d_values = sc.alloc<float>(n);
+  auto* d_pol = policies ? sc.alloc<float>((size_t)n * SPB_CHESS_POLICY_SIZE) : nullptr;
+  if (!d_states || (history && !d_hist) || !d_moves || !d_nmoves || !d_reps || !d_count || !d_logits || !d_values || (policies && !d_pol)) {
+    e->set_error("chess: out of device memory");
+    return SPB_ERR_NOMEM;
+  }
+  CH_CUDA(e, cudaMemcpyAsync(d_states, states, (size_t)n * sizeof(ch::Pos), cudaMemcpyHostToDevice, e->stream));
+  if (history) CH_CUDA(e, cudaMemcpyAsync(d_hist, history, (size_t)n * SPB_CHESS_MAX_HISTORY * 8, cudaMemcpyHostToDevice, e->stream));
+  CH_CUDA(e, cudaMemcpyAsync(d_count, &n, 4, cudaMemcpyHostToDevice, e->stream));
+  ch::k_predict_prepare<<<(n + 3) / 4, 128, 0, e->stream>>>(d_states, d_hist, n, d_moves, d_nmoves, d_reps, e->T.error);
+  CH_CUDA(e, cudaGetLastError());
+  uint32_t launched = 0;
+  const cudaError_t ce = ch::net_forward(e->net, d_states, d_reps, nullptr, d_count, d_logits, d_values, e->stream, &launched);
+  if (ce != cudaSuccess) { e->set_error(std::string("chess network launch: ") + cudaGetErrorString(ce)); return SPB_ERR_CUDA; }
+  e->launches += 1 + launched;
+  if (policies) {
+    ch::k_predict_mask<<<n, 256, 0, e->stream>>>(d_logits, d_states, d_moves, d_nmoves, n, d_pol);
+    CH_CUDA(e, cudaGetLastError());
+    ++e->launches;
+    CH_CUDA(e, cudaMemcpyAsync(policies, d_pol, (size_t)n * SPB_CHESS_POLICY_SIZE * 4, cudaMemcpyDeviceToHost, e->stream));
+  }
+  if (values) CH_CUDA(e, cudaMemcpyAsync(values, d_values, (size_t)n * 4, cudaMemcpyDeviceToHost, e->stream));
+  if (raw_logits) CH_CUDA(e, cudaMemcpyAsync(raw_logits, d_logits, (size_t)n * SPB_CHESS_POLICY_SIZE * 4, cudaMemcpyDeviceToHost, e->stream));
+  CH_CUDA(e, cudaStreamSynchronize(e->stream));
+  return e->check_device_errors();
+}
+
+}  // extern "C"

@@ -19,6 +19,7 @@
 #include <string>
 #include <vector>
 
+#include "chess_net.cuh"
 #include "evaluator.cuh"
 
 namespace spb {
@@ -253,4 +254,104 @@ bool parse_safetensors_net(const void* blob_v, size_t n, int game, HostNet* out,
   return true;
 }
 
+
+// ---- chess network (ref: src/model/chess.rs:50-73) -------------------------------------------------------------------
+// Explicit names: conv{i}.{weight,bias} + bn{i}.{weight,bias,running_mean,running_var} for i = 0 (stem), 1..20 (residual
+// convs); policy_conv1 / policy_conv2 / value_conv / value_fc1 / value_fc2 .{weight,bias}.  tch VarStore names: creation
+// order as for the small nets — torso (conv, bn) x 21, policy convs, value conv, the two Linear layers.
+namespace chess {
+
+bool parse_safetensors_chess(const void* blob_v, size_t n, HostNet* out, std::string* err) {
+  const uint8_t* blob = static_cast<const uint8_t*>(blob_v);
+  std::vector<TensorInfo> infos;
+  size_t data_off = 0;
+  if (!parse_header(blob, n, &infos, &data_off, err)) return false;
+  std::map<std::string, const TensorInfo*> by_name;
+  for (const auto& t : infos) by_name[t.name] = &t;
+  struct Raw { Loaded w, b, g, beta, mean, var; } conv[NET_CONV3];
+  Loaded p1w, p1b, p2w, p2b, vw, vb, f1w, f1b, f2w, f2b;
+  auto get = [&](const std::string& name, Loaded* dst) -> bool {
+    auto it = by_name.find(name);
+    if (it == by_name.end()) { *err = "missing tensor " + name; return false; }
+    return load_f32(blob, n, data_off, *it->second, dst, err);
+  };
+  if (by_name.count("conv0.weight")) {
+    for (int i = 0; i < NET_CONV3; ++i) {
+      const std::string c = "conv" + std::to_string(i), b = "bn" + std::to_string(i);
+      if (!get(c + ".weight", &conv[i].w) || !get(c + ".bias", &conv[i].b) || !get(b + ".weight", &conv[i].g) ||
+          !get(b + ".bias", &conv[i].beta) || !get(b + ".running_mean", &conv[i].mean) || !get(b + ".running_var", &conv[i].var))
+        return false;
+    }
+    if (!get("policy_conv1.weight", &p1w) || !get("policy_conv1.bias", &p1b) || !get("policy_conv2.weight", &p2w) ||
+        !get("policy_conv2.bias", &p2b) || !get("value_conv.weight", &vw) || !get("value_conv.bias", &vb) ||
+        !get("value_fc1.weight", &f1w) || !get("value_fc1.bias", &f1b) || !get("value_fc2.weight", &f2w) || !get("value_fc2.bias", &f2b))
+      return false;
+  } else {
+    struct Item { long idx; const TensorInfo* t; };
+    std::vector<Item> w4, w1, w2, bias, rmean, rvar;
+    for (const auto& t : infos) {
+      std::string base; long idx;
+      split_suffix(t.name, &base, &idx);
+      if (base == "weight") {
+        if (t.shape.size() == 4) w4.push_back({idx, &t});
+        else if (t.shape.size() == 1) w1.push_back({idx, &t});
+        else if (t.shape.size() == 2) w2.push_back({idx, &t});
+      } else if (base == "bias") bias.push_back({idx, &t});
+      else if (base == "running_mean") rmean.push_back({idx, &t});
+      else if (base == "running_var") rvar.push_back({idx, &t});
+    }
+    auto by_idx = [](const Item& a, const Item& b) { return a.idx < b.idx; };
+    for (auto* v : {&w4, &w1, &w2, &bias, &rmean, &rvar}) std::stable_sort(v->begin(), v->end(), by_idx);
+    if (w4.size() != NET_CONV3 + 3 || w1.size() != NET_CONV3 || rmean.size() != NET_CONV3 || rvar.size() != NET_CONV3 || w2.size() != 2 ||
+        bias.size() != 2 * NET_CONV3 + 5) {
+      *err = "unexpected tensor census for the chess 10x256 ResNet: conv weights " + std::to_string(w4.size()) + ", bn weights " +
+             std::to_string(w1.size()) + ", linear weights " + std::to_string(w2.size()) + ", biases " + std::to_string(bias.size());
+      return false;
+    }
+    int bi = 0;
+    for (int i = 0; i < NET_CONV3; ++i) {
+      if (!load_f32(blob, n, data_off, *w4[i].t, &conv[i].w, err) || !load_f32(blob, n, data_off, *w1[i].t, &conv[i].g, err) ||
+          !load_f32(blob, n, data_off, *rmean[i].t, &conv[i].mean, err) || !load_f32(blob, n, data_off, *rvar[i].t, &conv[i].var, err) ||
+          !load_f32(blob, n, data_off, *bias[bi++].t, &conv[i].b, err) || !load_f32(blob, n, data_off, *bias[bi++].t, &conv[i].beta, err))
+        return false;
+    }
+    if (!load_f32(blob, n, data_off, *w4[NET_CONV3].t, &p1w, err) || !load_f32(blob, n, data_off, *bias[bi++].t, &p1b, err) ||
+        !load_f32(blob, n, data_off, *w4[NET_CONV3 + 1].t, &p2w, err) || !load_f32(blob, n, data_off, *bias[bi++].t, &p2b, err) ||
+        !load_f32(blob, n, data_off, *w4[NET_CONV3 + 2].t, &vw, err) || !load_f32(blob, n, data_off, *bias[bi++].t, &vb, err) ||
+        !load_f32(blob, n, data_off, *w2[0].t, &f1w, err) || !load_f32(blob, n, data_off, *bias[bi++].t, &f1b, err) ||
+        !load_f32(blob, n, data_off, *w2[1].t, &f2w, err) || !load_f32(blob, n, data_off, *bias[bi++].t, &f2b, err))
+      return false;
+  }
+  for (int i = 0; i < NET_CONV3; ++i) {
+    const int ic = i == 0 ? NET_IN : NET_HIDDEN, oc = NET_HIDDEN;
+    if (!shape_is(conv[i].w, {oc, ic, 3, 3}) || !shape_is(conv[i].b, {oc}) || !shape_is(conv[i].g, {oc}) || !shape_is(conv[i].beta, {oc}) ||
+        !shape_is(conv[i].mean, {oc}) || !shape_is(conv[i].var, {oc})) {
+      *err = "shape mismatch in conv/bn layer " + std::to_string(i) + " of the chess net";
+      return false;
+    }
+    HostNet::Conv& h = out->conv3[i];
+    h.oc = oc; h.ic = ic; h.k = 3;
+    h.w.resize((size_t)oc * ic * 9);
+    h.b.resize(oc);
+    for (int o = 0; o < oc; ++o) {
+      const double s = (double)conv[i].g.data[o] / std::sqrt((double)conv[i].var.data[o] + (double)NET_BN_EPS);
+      for (int k = 0; k < ic * 9; ++k) h.w[(size_t)o * ic * 9 + k] = (float)((double)conv[i].w.data[(size_t)o * ic * 9 + k] * s);
+      h.b[o] = (float)(((double)conv[i].b.data[o] - (double)conv[i].mean.data[o]) * s + (double)conv[i].beta.data[o]);
+    }
+  }
+  if (!shape_is(p1w, {NET_HIDDEN, NET_HIDDEN, 1, 1}) || !shape_is(p1b, {NET_HIDDEN}) || !shape_is(p2w, {NET_MOVE_PLANES, NET_HIDDEN, 1, 1}) ||
+      !shape_is(p2b, {NET_MOVE_PLANES}) || !shape_is(vw, {1, NET_HIDDEN, 1, 1}) || !shape_is(vb, {1}) || !shape_is(f1w, {256, 64}) ||
+      !shape_is(f1b, {256}) || !shape_is(f2w, {1, 256}) || !shape_is(f2b, {1})) {
+    *err = "shape mismatch in the heads of the chess net";
+    return false;
+  }
+  auto set1x1 = [](HostNet::Conv& h, const Loaded& w, const Loaded& b, int oc) { h.oc = oc; h.ic = NET_HIDDEN; h.k = 1; h.w = w.data; h.b = b.data; };
+  set1x1(out->p1, p1w, p1b, NET_HIDDEN);
+  set1x1(out->p2, p2w, p2b, NET_MOVE_PLANES);
+  set1x1(out->vconv, vw, vb, 1);
+  out->fc1_w = f1w.data; out->fc1_b = f1b.data; out->fc2_w = f2w.data; out->fc2_b = f2b.data;
+  return true;
+}
+
+}  // namespace chess
 }  // namespace spb

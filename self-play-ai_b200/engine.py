@@ -10,7 +10,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = os.path.join(_HERE, "libselfplay_b200.so")
 
-GAME_TTT, GAME_C4 = 0, 1
+GAME_TTT, GAME_C4, GAME_CHESS = 0, 1, 2
 EVAL_NET, EVAL_DET, EVAL_UNIFORM = 0, 1, 2
 ONGOING, TIED, WON = 0, 1, 2
 MAX_ACTIONS = 9
@@ -99,7 +99,12 @@ ABI = {
     "spb_comm_destroy": (C.c_int32, [_vp]),
     "spb_gather_trajectories": (C.c_int32, [_vp, C.c_int32, _vp, C.c_size_t, C.POINTER(C.c_size_t), _vp]),
     "spb_positions_to_training": (C.c_int32, [C.c_int32, _vp, C.c_size_t, _vp, _vp, _vp]),
-    # chess (ref: src/game/chess.rs); typed wrappers in chess.py
+    # chess (ref: src/game/chess.rs, src/model/chess.rs); typed wrappers in chess.py
+    "spb_chess_create": (C.c_int32, [C.POINTER(Config), C.POINTER(_vp)]),
+    "spb_chess_destroy": (C.c_int32, [_vp]),
+    "spb_chess_last_error": (C.c_char_p, [_vp]),
+    "spb_chess_load_weights": (C.c_int32, [_vp, _vp, C.c_size_t]),
+    "spb_chess_check_weights": (C.c_int32, [_vp, C.c_size_t, C.c_char_p, C.c_size_t]),
     "spb_chess_start_position": (C.c_int32, [_vp]),
     "spb_chess_legal_moves": (C.c_int32, [_vp, _vp, _vp, C.c_uint32, _vp, _vp, _vp, _vp, _vp]),
     "spb_chess_next_states": (C.c_int32, [_vp, _vp, _vp, _vp, C.c_uint32, _vp, _vp]),
@@ -108,6 +113,19 @@ ABI = {
     "spb_chess_move_channel": (C.c_int32, [C.c_int32, C.c_uint16]),
     "spb_chess_policy_index": (C.c_int32, [C.c_int32, C.c_uint16]),
     "spb_chess_action": (C.c_uint16, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "spb_chess_reset_games": (C.c_int32, [_vp, _vp, C.c_uint32, _vp, _vp]),
+    "spb_chess_search": (C.c_int32, [_vp, C.c_uint32]),
+    "spb_chess_last_search_ms": (C.c_int32, [_vp, _f32p]),
+    "spb_chess_root_children": (C.c_int32, [_vp, C.c_uint32, _vp, _vp, _vp, _u32p]),
+    "spb_chess_root_children_all": (C.c_int32, [_vp, _vp, _vp, _vp, _vp]),
+    "spb_chess_root_policy": (C.c_int32, [_vp, C.c_uint32, _vp]),
+    "spb_chess_advance": (C.c_int32, [_vp, _vp, _vp, C.c_uint32, _vp]),
+    "spb_chess_get_state": (C.c_int32, [_vp, C.c_uint32, C.c_uint32, _vp]),
+    "spb_chess_arena_len": (C.c_int32, [_vp, C.c_uint32, _u32p]),
+    "spb_chess_node_stats": (C.c_int32, [_vp, C.c_uint32, C.c_uint32, _u32p, _f32p, _f32p, _u32p, _u32p, C.POINTER(C.c_uint16), _u8p]),
+    "spb_chess_predict": (C.c_int32, [_vp, _vp, _vp, C.c_uint32, _vp, _vp, _vp]),
+    "spb_chess_get_counters": (C.c_int32, [_vp, C.POINTER(Counters)]),
+    "spb_chess_reset_counters": (C.c_int32, [_vp]),
     "spb_get_counters": (C.c_int32, [_vp, C.POINTER(Counters)]),
     "spb_reset_counters": (C.c_int32, [_vp]),
     "spb_last_search_timing": (C.c_int32, [_vp, _f32p, _f32p, _u32p]),

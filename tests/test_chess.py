@@ -212,8 +212,8 @@ def export_all(games):
 
 @pytest.fixture(scope="module")
 def rules():
-    with S.Engine(game=S.GAME_C4, num_games=1, evaluator=S.EVAL_DET) as e:
-        yield S.ChessRules(e)
+    with S.ChessEngine(num_games=1, evaluator=S.EVAL_DET) as e:
+        yield e
 
 
 @pytest.mark.gpu
