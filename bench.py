@@ -5,6 +5,7 @@
     python bench.py --impl reference ...                   # the reference's algorithm on the host CPU cores
     python bench.py --leaves 16                            # configs[3]: 16 leaves in flight per tree (virtual loss, lock-step)
     python bench.py --game ttt --sims 600                  # configs[0]: tic-tac-toe
+    python bench.py --game chess                           # configs[4]: chess, 200 sims/move, the 10x256 net (lock-step)
 
 One "step" = one `search` call (ref: Mcts::search, src/mcts.rs:196) of 800 simulations over 4,096 concurrent
 Connect4 games per GPU, every tree fresh at a seeded synthetic root, evaluator = the
@@ -419,20 +420,202 @@ def run_ours(args):
     return 0
 
 
+# -------------------------------------------------------------------------------------------------
+# chess (BASELINE.json configs[4]): bitboard move generation + MCTS at 200 sims/move with the 10x256 net
+# -------------------------------------------------------------------------------------------------
+CHESS_SIMS = 200
+CHESS_GAMES_PER_GPU = 4096
+CHESS_MAX_PLY = 41
+
+
+class ChessCpuArm(CpuArm):
+    """The CPU arm for chess: oracle/chess_cpu_worker.py processes (oracle MCTS over chess + torch CPU fp32 net)."""
+
+    def __init__(self, sims: int, blob: bytes, games_per_worker: int, workers: int | None = None, segment: int = 4):
+        import tempfile
+        self.workers = workers or (os.cpu_count() or 1)
+        self.sims, self.segment, self.games = sims, min(segment, sims), games_per_worker
+        self.done_on_trees = 0
+        self.tmp = tempfile.NamedTemporaryFile(suffix=".safetensors", delete=False)
+        self.tmp.write(blob)
+        self.tmp.close()
+        env = dict(os.environ, OMP_NUM_THREADS="1", MKL_NUM_THREADS="1")
+        self.procs = [subprocess.Popen([sys.executable, os.path.join(ROOT, "oracle", "chess_cpu_worker.py"), str(w), str(games_per_worker),
+                                        self.tmp.name, str(CHESS_MAX_PLY)], stdin=subprocess.PIPE, stdout=subprocess.PIPE,
+                                       stderr=subprocess.DEVNULL, text=True, env=env) for w in range(self.workers)]
+        for p in self.procs:
+            if p.stdout.readline().strip() != "ready":
+                raise RuntimeError("chess CPU worker failed to start")
+
+    def sample(self):
+        return ("%d worker processes x %d games, each step = %d consecutive simulations per tree from the seeded roots (a bounded "
+                "sample of the %d-simulation search: the first simulations of every tree); torch CPU fp32 10x256 net, 1 intra-op thread "
+                "per worker" % (self.workers, self.games, self.segment, self.sims))
+
+
+def chess_workload(games, sims):
+    return "chess_8x8_bitboard_movegen_mcts_%d_games_x_%d_sims_per_gpu" % (games, sims)
+
+
+def run_chess_reference(args):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return 0
+    from selfplay_b200.weights_init import random_chess_checkpoint
+    arm = ChessCpuArm(args.sims, random_chess_checkpoint(0), games_per_worker=8, segment=args.ref_segment if args.ref_segment != REF_SEGMENT else 4)
+    tot = [0, 0, 0, 0.0]
+    try:
+        for i in range(args.warmup + args.steps):
+            r = arm.step()
+            if i >= args.warmup:
+                tot = [a + b for a, b in zip(tot, r)]
+    finally:
+        sample, threads = arm.sample(), arm.workers
+        arm.close()
+    value = tot[0] / tot[3]
+    print(json.dumps({
+        "impl": "reference", "metric": "MCTS simulations/sec (whole box) chess @%d sims/move" % args.sims, "value": value, "unit": "sims/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot[3] / max(1, args.steps),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": chess_workload(args.games, args.sims), "sample": sample,
+                   "reference_arm": "oracle port of src/mcts.rs + src/game/chess.rs (no rustc/cargo here), evaluator = torch CPU fp32"},
+        "cpu_baseline": {"value": value, "unit": "sims/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "sims/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}), flush=True)
+    return 0
+
+
+def run_chess(args):
+    import torch
+    import torch.distributed as dist
+
+    import selfplay_b200 as S
+    from selfplay_b200.synth import synthetic_chess_roots_device
+    from selfplay_b200.weights_init import random_chess_checkpoint
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200; there is no CPU fallback (use --impl reference for the CPU arm)")
+    G, sims = args.games, args.sims
+    blob = random_chess_checkpoint(0)
+    eng = S.ChessEngine(num_games=G, evaluator=S.EVAL_NET, device=local_rank, max_nodes_per_tree=1024 * ((64 * sims + 2048) // 1024))
+    eng.load_weights(blob)
+    roots, hist = synthetic_chess_roots_device(eng, G, start=rank * G, max_ply=CHESS_MAX_PLY)   # games sharded by rank
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def rank_max(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(args.warmup):
+        eng.reset_games(roots, hist)
+        eng.search(sims)
+        eng.root_children_all()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    eng.reset_counters()
+    barrier()
+    dev_ms, t0 = 0.0, time.perf_counter()
+    for _ in range(args.steps):
+        eng.reset_games(roots, hist)
+        eng.search(sims)
+        dev_ms += eng.last_search_ms()
+    barrier()
+    wall_s = rank_max(time.perf_counter() - t0)
+    ctr = eng.counters()
+    dev_ms = rank_max(dev_ms)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        eng.reset_games(roots, hist)                        # H2D: states + game histories
+        eng.search(sims)
+        mv, cnt, ids, ncs = eng.root_children_all()         # D2H: moves, visit counts, child ids
+    barrier()
+    e2e_s = rank_max(time.perf_counter() - t0)
+    clocks = sampler.stop()
+    assert int(cnt[0].sum()) == sims - 1
+    peak_tf, peak_hbm, peak_src = _peaks()
+    conv_ms, conv_n, conv_flops, flops_pos = eng.time_conv(iters=20)
+    total_sims = world * G * sims * args.steps
+    achieved = conv_flops / (conv_ms * 1e-3) / 1e12
+    evals = ctr["evaluations"]
+    line = {
+        "metric": "MCTS simulations/sec (whole box) chess @%d sims/move" % sims, "value": total_sims / (dev_ms * 1e-3), "unit": "sims/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": chess_workload(G, sims), "games_per_gpu": G, "sims_per_move": sims, "leaves_per_tree": 1,
+                   "pipeline": "lock-step (the reference's loop: select over all trees, one network batch, expand + backup)",
+                   "evaluator": "chess 10x256 conv ResNet, random init (numpy seed 0), BN folded, bf16 operands / f32 accumulate",
+                   "roots": "seeded random playouts of 0..%d plies from the start position (device rules)" % (CHESS_MAX_PLY - 1),
+                   "parallelism": "games sharded by rank, no collective on the search path",
+                   "cache": "inputs larger than L2: activations of one layer %d MB, node pools touched ~%d MB" % (
+                       G * 81 * 512 // (1 << 20), ctr["nodes_live"] * 32 // (1 << 20)),
+                   "timing": "CUDA events on the engine stream around each search, max over ranks; wall clock %.3f s" % wall_s},
+        "e2e": {"value": total_sims / e2e_s, "unit": "sims/s", "h2d_bytes_per_step": int(roots.nbytes + hist.nbytes),
+                "d2h_bytes_per_step": int(mv.nbytes + cnt.nbytes + ids.nbytes + ncs.nbytes)},
+        "gpu_launches": int(ctr["kernel_launches"]),
+        "clocks": clocks,
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None,
+                     "kernel": "chess::k_conv<8, 9, 256> (one 256->256 3x3 residual convolution over the leaf batch; 20 of the 25 launches "
+                               "per evaluation and 99 % of its FLOPs)",
+                     "peak_source": peak_src, "positions_per_launch": conv_n, "flops_per_launch": conv_flops, "avg_launch_ms": conv_ms,
+                     "useful_row_fraction": 64.0 / 81.0,
+                     "whole_network": {"flops_per_position": flops_pos,
+                                       "tflops_over_search": flops_pos * evals / (dev_ms * 1e-3) / 1e12,
+                                       "note": "all evaluations x FLOPs per evaluation / device time of the searches (tree kernels included)"}},
+        "counters": {k: ctr[k] for k in ("simulations", "evaluations", "terminal_leaves")},
+        "tree_side": {"mean_path_length": ctr["path_length_sum"] / max(1, ctr["simulations"]),
+                      "mean_branching": ctr["children_created"] / max(1, ctr["evaluations"]), "largest_arena": ctr["largest_arena"]},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        eng.close()
+        arm = ChessCpuArm(sims, blob, games_per_worker=8)
+        tot = [0, 0, 0, 0.0]
+        try:
+            for _ in range(3):
+                tot = [a + b for a, b in zip(tot, arm.step())]
+        finally:
+            sample, threads = arm.sample(), arm.workers
+            arm.close()
+        line["cpu_baseline"] = {"value": tot[0] / tot[3], "unit": "sims/s", "cores": threads, "kind": "port", "sample": sample}
+    else:
+        line["cpu_baseline"] = None
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--games", type=int, default=GAMES_PER_GPU)
-    ap.add_argument("--sims", type=int, default=SIMS)
+    ap.add_argument("--games", type=int, default=None)
+    ap.add_argument("--sims", type=int, default=None)
     ap.add_argument("--ref-segment", type=int, default=REF_SEGMENT, help="CPU arm: simulations per step (consecutive segments of one --sims search)")
     ap.add_argument("--leaves", type=int, default=1, help="leaves in flight per tree (configs[3]: 16); > 1 runs the lock-step virtual-loss pipeline")
-    ap.add_argument("--game", default="c4", choices=["c4", "ttt"], help="configs[0] is tic-tac-toe")
+    ap.add_argument("--game", default="c4", choices=["c4", "ttt", "chess"], help="configs[0] is tic-tac-toe, configs[4] chess")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--full-game-moves", type=int, default=4, help="extra leg: self-play moves with subtree reuse (0 = skip)")
     args = ap.parse_args()
+    if args.games is None:
+        args.games = CHESS_GAMES_PER_GPU if args.game == "chess" else GAMES_PER_GPU
+    if args.sims is None:
+        args.sims = CHESS_SIMS if args.game == "chess" else SIMS
     if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
         # not under torchrun: launch one rank per GPU ourselves
         import socket
@@ -447,6 +630,8 @@ def main():
     json_fd = os.dup(1)
     os.dup2(2, 1)
     sys.stdout = os.fdopen(json_fd, "w")
+    if args.game == "chess":
+        return run_chess_reference(args) if args.impl == "reference" else run_chess(args)
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)

@@ -354,6 +354,14 @@ int32_t spb_chess_node_stats(spb_chess_engine* e, uint32_t slot, uint32_t node_i
  * (chess.rs:251-271), values[n], raw_logits[n][4672] (each nullable).  n <= num_games. */
 int32_t spb_chess_predict(spb_chess_engine* e, const spb_chess_state* states, const uint64_t* history, uint32_t n, float* policies, float* values,
                           float* raw_logits);
+/*
+ * Re-runs the dominant kernel — one 256 -> 256 3x3 residual convolution over the evaluator batch of the most recent
+ * spb_chess_search, still resident in HBM — `iters` times between CUDA events on the engine's stream: average launch
+ * duration, positions in the batch, algorithmic FLOPs of one launch (2*MAC) and of a whole network evaluation per position.
+ * Used by bench.py for the tensor roofline.
+ */
+int32_t spb_chess_time_conv(spb_chess_engine* e, uint32_t iters, float* avg_ms, uint32_t* n_positions, double* flops_per_launch,
+                            double* flops_per_position);
 int32_t spb_chess_get_counters(spb_chess_engine* e, spb_counters* out);   /* reserved[0] = largest arena */
 int32_t spb_chess_reset_counters(spb_chess_engine* e);
 

@@ -256,3 +256,36 @@ def chess_forward(net, enc):
         x = torch.from_numpy(np.ascontiguousarray(enc, dtype=np.float32))
         p, v = net(x)
         return torch.softmax(p, -1).numpy(), v.reshape(-1).numpy(), p.numpy()
+
+
+def load_chess_tch_safetensors(blob: bytes):
+    """Builds the torch chess net from a tch-style checkpoint (creation-order names)."""
+    hlen = struct.unpack("<Q", blob[:8])[0]
+    header = json.loads(blob[8:8 + hlen])
+    data = blob[8 + hlen:]
+    items = []
+    for name, meta in header.items():
+        if name == "__metadata__":
+            continue
+        base, _, idx = name.partition("__")
+        arr = np.frombuffer(data[meta["data_offsets"][0]:meta["data_offsets"][1]], dtype=np.float32).reshape(meta["shape"])
+        items.append((int(idx) if idx else -1, base, arr))
+    items.sort(key=lambda t: t[0])
+    net = ChessNet().eval()
+    it = iter(items)
+
+    def take(n):
+        got = {}
+        for _ in range(n):
+            _, base, arr = next(it)
+            got[base] = torch.from_numpy(arr.copy())
+        return got
+    with torch.no_grad():
+        def fill_wb(m):
+            g = take(2); m.weight.copy_(g["weight"]); m.bias.copy_(g["bias"])
+        for c, b in net.conv_bn_pairs():
+            fill_wb(c)
+            g = take(4); b.weight.copy_(g["weight"]); b.bias.copy_(g["bias"]); b.running_mean.copy_(g["running_mean"]); b.running_var.copy_(g["running_var"])
+        for m in (net.p1, net.p2, net.vconv, net.fc1, net.fc2):
+            fill_wb(m)
+    return net

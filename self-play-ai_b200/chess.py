@@ -213,6 +213,13 @@ class ChessEngine:
         return dict(visit_count=n.value, value_sum=w.value, prior=p.value, first_child=fc.value, n_children=nc.value, move=mv.value,
                     status=st.value)
 
+    def time_conv(self, iters=20):
+        """-> (avg launch ms, positions in the batch, FLOPs per launch, FLOPs per evaluated position) of the residual conv kernel
+        re-run on the last evaluator batch (spb_chess_time_conv)."""
+        ms, n, fl, fp = C.c_float(), C.c_uint32(), C.c_double(), C.c_double()
+        self._chk(self._L.spb_chess_time_conv(self._h, iters, C.byref(ms), C.byref(n), C.byref(fl), C.byref(fp)))
+        return ms.value, n.value, fl.value, fp.value
+
     def counters(self) -> dict:
         c = E.Counters()
         self._chk(self._L.spb_chess_get_counters(self._h, C.byref(c)))

@@ -295,18 +295,22 @@ __global__ void __launch_bounds__(THREADS) k_chess_advance(CTrees T, const uint3
     nhash[0] = ohash[id];
   }
   __syncwarp();
-  uint32_t n_new = 1;
-  for (uint32_t j0 = 0; j0 < n_new; j0 += 32) {
+  uint32_t n_new = 1, j0 = 0;
+  while (j0 < n_new) {
+    const uint32_t in_window = min(32u, n_new - j0);                   // nodes copied so far that still await their turn
     const uint32_t j = j0 + lane;
     uint32_t nc = 0, old_fc = 0;
-    if (j < n_new) {
+    if ((uint32_t)lane < in_window) {
       const uint32_t my = nmeta[j].y;
       if (meta_status(my) == ST_EXPANDED) { nc = meta_nc(my); old_fc = nrec[j].w; }
     }
     int total;
     const uint32_t new_fc = n_new + (uint32_t)warp_excl_scan((int)nc, lane, &total);
+    if (n_new + (uint32_t)total > T.cap) {                             // cannot happen: the subtree is part of an arena of <= cap nodes
+      if (lane == 0) atomicOr(T.error, (uint32_t)ERRBIT_BOUNDS | (43u << 8));
+      break;
+    }
     if (nc) nrec[j].w = new_fc;
-    const uint32_t in_window = min(32u, n_new - j0);
     for (uint32_t l = 0; l < in_window; ++l) {
       const uint32_t cnc = __shfl_sync(0xffffffffu, nc, l), cold = __shfl_sync(0xffffffffu, old_fc, l), cnew = __shfl_sync(0xffffffffu, new_fc, l);
       for (uint32_t k = lane; k < cnc; k += 32) {
@@ -316,6 +320,7 @@ __global__ void __launch_bounds__(THREADS) k_chess_advance(CTrees T, const uint3
       }
     }
     n_new += (uint32_t)total;
+    j0 += in_window;
     __syncwarp();
   }
   if (lane == 0) {

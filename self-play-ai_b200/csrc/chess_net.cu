@@ -469,6 +469,25 @@ cudaError_t net_forward(Net* net, const Pos* pos, const uint32_t* reps, const ui
   return cudaSuccess;
 }
 
+// Re-runs one residual convolution (k_conv<8, 9, 256, EPI_RELU>: x -> y, layer 1; y is scratch between blocks) on the
+// activations the last forward left in HBM, `iters` launches between two CUDA events on `stream`.
+cudaError_t net_time_conv(Net* net, const uint32_t* count_dev, uint32_t iters, cudaStream_t stream, cudaEvent_t ev0, cudaEvent_t ev1, float* avg_ms) {
+  ConvArgs a{};
+  a.count = count_dev; a.plane_rows = (uint32_t)net->plane_rows;
+  a.in = net->d_x; a.out = net->d_y; a.w = net->d_w + net->off_conv[1]; a.bias = net->d_f + net->off_bias[1];
+  cudaError_t e;
+  if ((e = launch_conv<8, 9, 256, EPI_RELU>(net, a, stream)) != cudaSuccess) return e;   // warm
+  if ((e = cudaEventRecord(ev0, stream)) != cudaSuccess) return e;
+  for (uint32_t i = 0; i < iters; ++i)
+    if ((e = launch_conv<8, 9, 256, EPI_RELU>(net, a, stream)) != cudaSuccess) return e;
+  if ((e = cudaEventRecord(ev1, stream)) != cudaSuccess) return e;
+  if ((e = cudaEventSynchronize(ev1)) != cudaSuccess) return e;
+  float ms = 0.f;
+  if ((e = cudaEventElapsedTime(&ms, ev0, ev1)) != cudaSuccess) return e;
+  *avg_ms = ms / (float)iters;
+  return cudaSuccess;
+}
+
 int32_t net_forward_leaves(spb_chess_engine* e, uint32_t* launched) {
   const cudaError_t ce = net_forward(e->net, e->T.leaf_pos, e->T.leaf_reps, e->T.eval_list, e->T.eval_count, e->T.eval_logits, e->T.eval_value,
                                      e->stream, launched);
@@ -564,6 +583,24 @@ int32_t spb_chess_check_weights(const void* blob, size_t n, char* err, size_t er
     if (err && err_cap) { std::strncpy(err, msg.c_str(), err_cap - 1); err[err_cap - 1] = 0; }
     return SPB_ERR_WEIGHTS;
   }
+  return SPB_OK;
+}
+
+int32_t spb_chess_time_conv(spb_chess_engine* e, uint32_t iters, float* avg_ms, uint32_t* n_positions, double* flops_per_launch,
+                            double* flops_per_position) {
+  CH_GUARD(e);
+  CH_ARG(e, avg_ms && n_positions && flops_per_launch && flops_per_position && iters > 0, "bad argument");
+  CH_ARG(e, e->net && ch::net_loaded(e->net), "no weights loaded (spb_chess_load_weights)");
+  uint32_t n = 0;
+  CH_CUDA(e, cudaMemcpyAsync(&n, e->T.eval_count, 4, cudaMemcpyDeviceToHost, e->stream));
+  CH_CUDA(e, cudaStreamSynchronize(e->stream));
+  CH_ARG(e, n > 0, "no evaluator batch resident (run spb_chess_search first)");
+  const cudaError_t ce = ch::net_time_conv(e->net, e->T.eval_count, iters, e->stream, e->ev0, e->ev1, avg_ms);
+  if (ce != cudaSuccess) { e->set_error(std::string("chess conv timing: ") + cudaGetErrorString(ce)); return SPB_ERR_CUDA; }
+  e->launches += iters + 1;
+  *n_positions = n;
+  *flops_per_launch = (double)n * 2.0 * 64 * 256 * 9 * 256;
+  *flops_per_position = ch::net_flops_per_position();
   return SPB_OK;
 }
 

@@ -124,6 +124,7 @@ ABI = {
     "spb_chess_arena_len": (C.c_int32, [_vp, C.c_uint32, _u32p]),
     "spb_chess_node_stats": (C.c_int32, [_vp, C.c_uint32, C.c_uint32, _u32p, _f32p, _f32p, _u32p, _u32p, C.POINTER(C.c_uint16), _u8p]),
     "spb_chess_predict": (C.c_int32, [_vp, _vp, _vp, C.c_uint32, _vp, _vp, _vp]),
+    "spb_chess_time_conv": (C.c_int32, [_vp, C.c_uint32, _f32p, _u32p, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "spb_chess_get_counters": (C.c_int32, [_vp, C.POINTER(Counters)]),
     "spb_chess_reset_counters": (C.c_int32, [_vp]),
     "spb_get_counters": (C.c_int32, [_vp, C.POINTER(Counters)]),

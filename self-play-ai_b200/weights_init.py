@@ -57,3 +57,45 @@ def random_checkpoint(game: int, seed: int = 0, blocks: int = 4, hidden: int = 6
     hj = json.dumps(header, separators=(",", ":")).encode()
     hj += b" " * ((8 - len(hj) % 8) % 8)
     return struct.pack("<Q", len(hj)) + hj + b"".join(chunks)
+
+
+def random_chess_checkpoint(seed: int = 0, blocks: int = 10, hidden: int = 256) -> bytes:
+    """Random-init checkpoint of the chess net (ref: src/model/chess.rs:50-73) with tch's creation-order names:
+    torso (conv, bn) x 21, policy head conv1x1 256->256, conv1x1 256->73, value head conv1x1 256->1, Linear 64->256,
+    Linear 256->1."""
+    rng = np.random.default_rng(seed)
+    created = []
+
+    def conv(ic, oc, k):
+        created.append(("bias", _uniform(rng, (oc,), ic * k * k)))
+        created.append(("weight", _uniform(rng, (oc, ic, k, k), ic * k * k)))
+
+    def bn(c):
+        created.append(("weight", np.ones(c, np.float32)))
+        created.append(("bias", np.zeros(c, np.float32)))
+        created.append(("running_mean", np.zeros(c, np.float32)))
+        created.append(("running_var", np.ones(c, np.float32)))
+
+    def linear(i, o):
+        created.append(("bias", _uniform(rng, (o,), i)))
+        created.append(("weight", _uniform(rng, (o, i), i)))
+
+    conv(19, hidden, 3); bn(hidden)
+    for _ in range(blocks):
+        conv(hidden, hidden, 3); bn(hidden)
+        conv(hidden, hidden, 3); bn(hidden)
+    conv(hidden, 256, 1); conv(256, 73, 1)
+    conv(hidden, 1, 1); linear(64, 256); linear(256, 1)
+
+    header, chunks, off, seen, count = {}, [], 0, set(), 0
+    for base, arr in created:
+        name = base if base not in seen else "%s__%d" % (base, count)
+        seen.add(base)
+        count += 1
+        b = np.ascontiguousarray(arr, dtype=np.float32).tobytes()
+        header[name] = {"dtype": "F32", "shape": list(arr.shape), "data_offsets": [off, off + len(b)]}
+        off += len(b)
+        chunks.append(b)
+    hj = json.dumps(header, separators=(",", ":")).encode()
+    hj += b" " * ((8 - len(hj) % 8) % 8)
+    return struct.pack("<Q", len(hj)) + hj + b"".join(chunks)

@@ -105,8 +105,53 @@ def test_flag_and_code_constants_agree_across_header_python_and_rust():
     flags = [v for k, v in defs.items() if k.startswith("SPB_FLAG_")]
     assert len(set(flags)) == len(flags) and all(v & (v - 1) == 0 for v in flags)      # distinct single bits
     rust = open(os.path.join(root, "rust", "selfplay-b200-sys", "src", "lib.rs")).read()
-    for m in re.finditer(r"pub const (SPB_[A-Z0-9_]+): [iu]32 = (-?\d+);", rust):
+    n_consts = 0
+    for m in re.finditer(r"pub const (SPB_[A-Z0-9_]+): (?:[iu]32|u8|usize) = (-?\d+);", rust):
         assert defs[m.group(1)] == int(m.group(2)), m.group(1)
+        n_consts += 1
+    assert n_consts >= 30
+
+
+def test_rust_sys_crate_mirrors_every_function_and_struct_of_the_header():
+    """rust/selfplay-b200-sys cannot be compiled here (no rustc), so its text is checked against the header: the same set of
+    functions with the same number of parameters, and the same struct fields in the same order with matching types."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    rust = open(os.path.join(root, "rust", "selfplay-b200-sys", "src", "lib.rs")).read()
+    # functions
+    c_fns = {}
+    for m in re.finditer(r"\b(?:int32_t|uint16_t|const char\*)\s+(spb_[a-z_0-9]+)\s*\(([^;]*?)\)\s*;", HEADER, re.S):
+        args = re.sub(r"/\*.*?\*/", "", m.group(2), flags=re.S).strip()
+        c_fns[m.group(1)] = 0 if args in ("", "void") else args.count(",") + 1
+    r_fns = {}
+    for m in re.finditer(r"pub fn (spb_[a-z_0-9]+)\(([^)]*)\)", rust):
+        args = m.group(2).strip()
+        r_fns[m.group(1)] = 0 if not args else args.count(",") + 1
+    assert set(c_fns) == set(declared_symbols())
+    assert c_fns == r_fns, {k: (c_fns.get(k), r_fns.get(k)) for k in set(c_fns) | set(r_fns) if c_fns.get(k) != r_fns.get(k)}
+    # structs
+    ctype = {"uint64_t": "u64", "uint32_t": "u32", "uint16_t": "u16", "uint8_t": "u8", "int8_t": "i8", "int32_t": "i32", "float": "f32"}
+    size = {"u64": 8, "u32": 4, "u16": 2, "u8": 1, "i8": 1, "i32": 4, "f32": 4}
+    defs = {m.group(1): int(m.group(2).rstrip("u"), 0) for m in re.finditer(r"#define\s+(SPB_[A-Z0-9_]+)\s+(-?\d+u?)\b", HEADER)}
+    want_size = {"spb_state": 24, "spb_config": 64, "spb_counters": 96, "spb_position": 56, "spb_chess_state": 80}
+    for name in want_size:
+        body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (name, name), HEADER, re.S).group(1)
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        c_fields = []
+        for m in re.finditer(r"(\w+)\s+(\w+)(?:\[(\w+)\])?;", body):
+            n = m.group(3)
+            c_fields.append((m.group(2), ctype[m.group(1)], None if n is None else (int(n) if n.isdigit() else defs[n])))
+        rbody = re.search(r"pub struct %s \{(.*?)\n\}" % name, rust, re.S).group(1)
+        r_fields = []
+        for m in re.finditer(r"pub (\w+): (?:\[(\w+); (\w+)\]|(\w+)),", rbody):
+            if m.group(2):
+                n = m.group(3)
+                r_fields.append((m.group(1), m.group(2), int(n) if n.isdigit() else defs[n]))
+            else:
+                r_fields.append((m.group(1), m.group(4), None))
+        assert c_fields == r_fields, (name, c_fields, r_fields)
+        # natural alignment, no padding inside: the sum of the field sizes is the struct size both sides assume
+        assert sum(size[t] * (n or 1) for _, t, n in c_fields) == want_size[name], name
+    assert re.search(r"#\[repr\(C\)\]\s*(?:#\[derive[^\]]*\]\s*)?pub struct spb_chess_state", rust)
 
 
 def test_positions_to_training_matches_the_oracle_encodings():
