@@ -60,13 +60,25 @@ class Net(nn.Module):
         return pairs
 
 
-def make_net(game, seed=0, randomize_bn=True):
+def make_net(game, seed=0, randomize_bn=True, trained_like=False):
     """game: 0 tic-tac-toe, 1 connect4.  Default torch init under manual_seed; BN running stats and affine
-    parameters are randomised (when asked) so that BN folding is actually exercised."""
+    parameters are randomised (when asked) so that BN folding is actually exercised.  trained_like: statistics of a net
+    that has been trained for a while instead of a fresh one — BatchNorm gammas spread over 0.5..2, shifted and scaled
+    running statistics, larger head weights (logits of several units, tanh driven towards saturation)."""
     rows, cols, actions = (6, 7, 7) if game == 1 else (3, 3, 9)
     g = torch.Generator().manual_seed(seed)
     torch.manual_seed(seed)
     net = Net(rows, cols, actions).eval()
+    if trained_like:
+        with torch.no_grad():
+            for _, bn in net.conv_bn_pairs():
+                bn.running_mean.copy_(torch.randn(bn.num_features, generator=g) * 0.5)
+                bn.running_var.copy_(torch.rand(bn.num_features, generator=g) * 1.8 + 0.2)
+                bn.weight.copy_(torch.rand(bn.num_features, generator=g) * 1.5 + 0.5)
+                bn.bias.copy_(torch.randn(bn.num_features, generator=g) * 0.3)
+            net.pfc.weight.mul_(4.0)
+            net.vfc.weight.mul_(2.0)
+        return net
     if randomize_bn:
         with torch.no_grad():
             for _, bn in net.conv_bn_pairs():

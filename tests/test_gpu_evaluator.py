@@ -12,8 +12,8 @@ pytestmark = pytest.mark.gpu
 RTOL = 1e-2
 
 
-def _check(game, flags, n, seed, blob_fn):
-    net = torch_net.make_net(game, seed=seed)
+def _check(game, flags, n, seed, blob_fn, trained_like=False):
+    net = torch_net.make_net(game, seed=seed, trained_like=trained_like)
     states = random_states(game, n, seed=seed + 1, include_terminal=False)
     enc = np.stack([O.encode(game, s) for s in states])
     probs_ref, v_ref, logit_ref = torch_net.forward_probs(net, enc)
@@ -23,6 +23,12 @@ def _check(game, flags, n, seed, blob_fn):
     scale = float(np.abs(logit_ref).max())
     assert np.allclose(lg, logit_ref, rtol=RTOL, atol=RTOL * scale), float(np.abs(lg - logit_ref).max())
     assert np.allclose(v, v_ref, rtol=RTOL, atol=RTOL), float(np.abs(v - v_ref).max())
+    # the same bound per position, without the batch-wide scale: the error vector of a position's logits is within 1e-2 of
+    # the length of its logit vector, and the softmax it feeds moves no probability by more than 1e-2
+    rel_l2 = np.linalg.norm(lg - logit_ref, axis=1) / np.maximum(np.linalg.norm(logit_ref, axis=1), 1e-6)
+    assert rel_l2.max() <= RTOL, float(rel_l2.max())
+    e = np.exp(lg - lg.max(1, keepdims=True))
+    assert np.abs(e / e.sum(1, keepdims=True) - probs_ref).max() <= RTOL
     want_pol = np.stack([O.mask_invalid_actions(game, s, p) for s, p in zip(states, probs_ref)])
     assert np.allclose(pol, want_pol, rtol=5 * RTOL, atol=1e-3)
     assert np.allclose(pol.sum(1), 1.0, atol=1e-5)
@@ -42,6 +48,14 @@ def test_simt_evaluator_matches_torch(game):
 @pytest.mark.parametrize("n", [1, 9, 10, 300, 2000])
 def test_tcgen05_evaluator_matches_torch(game, n):
     _check(game, 0, n, 2, torch_net.to_safetensors_tch)
+
+
+@pytest.mark.parametrize("game", [S.GAME_C4, S.GAME_TTT], ids=["c4", "ttt"])
+def test_tcgen05_evaluator_matches_torch_on_a_trained_like_net(game):
+    """BatchNorm gammas 0.5..2, shifted running statistics, head weights x4 / x2 (tanh near saturation): the statistics of a
+    trained net rather than of a fresh one."""
+    lg, v = _check(game, 0, 600, 7, torch_net.to_safetensors_tch, trained_like=True)
+    assert np.abs(lg).max() > 1.0 and (np.abs(v) > 0.9).mean() > 0.05      # the net really is in that regime
 
 
 def test_tcgen05_and_simt_agree_closely():

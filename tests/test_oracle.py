@@ -249,3 +249,18 @@ def test_callback_evaluator_matches_builtin():
     f = O.Forest(O.GAME_C4, 2)
     f.search(100, O.EVAL_NET, cb)
     assert f.root_children(0)[1] == KAT["c4_det"]["100"] == f.root_children(1)[1]
+
+
+def test_committed_golden_vectors_come_from_the_generator():
+    """tests/golden/pyref_kats.json is the output of tools/gen_golden.py (the pure-Python restatement); every vector that
+    SURVEY.md §8(c) lists (survey_kats.json) equals it, and a re-run of one generator case reproduces the committed value."""
+    gen = json.load(open(os.path.join(HERE, "golden", "pyref_kats.json")))
+    for k, v in KAT.items():
+        if k != "_source":
+            assert gen[k] == v, k
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("gen_golden", os.path.join(os.path.dirname(HERE), "tools", "gen_golden.py"))
+    g = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(g)
+    assert g.counts(g.R.C4, 100, g.R.det_eval).root_counts() == gen["c4_det"]["100"]
+    assert g.greedy(g.R.C4, 200, g.R.det_eval)["actions"] == gen["c4_det_greedy_200"]["actions"]
