@@ -364,16 +364,6 @@ SPB_HD Move action(int side, int ch, int row, int col) {
   return make_move_code(row * 8 + col, r2 * 8 + c2, promo);
 }
 
-// perft: number of leaf positions of the legal-move tree of depth d (the standard move-generator test).
-SPB_HD uint64_t perft(const Pos& p, int depth) {
-  Move mv[MAX_MOVES];
-  const int n = legal_moves(p, mv);
-  if (depth <= 1) return depth == 1 ? (uint64_t)n : 1ull;
-  uint64_t total = 0;
-  for (int i = 0; i < n; ++i) total += perft(apply_move(p, mv[i]), depth - 1);
-  return total;
-}
-
 SPB_HD Pos start_position() {
   Pos p{};
   p.piece[PAWN] = RANK_2 | RANK_7;

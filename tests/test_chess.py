@@ -5,6 +5,8 @@ PARITY UNPINNED BY THE REFERENCE where the un-vendored crate `chess 3.2.0` decid
 src/game/chess.rs computes itself — repetition on legal-move lists (:51-62), the reversible-move counter (:124-143), get_status
 (:154-166), +1.0 for Won (:168-174), the 19x8x8 encoding (:176-249), the 73 move planes (:311-493) — is checked line by line.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -286,3 +288,58 @@ def test_device_handles_empty_and_single_batches(rules):
     assert rules.legal_moves(st[:0], hist[:0])[1].shape == (0,)
     moves, counts, _, status, reps = rules.legal_moves(st, None)
     assert counts[0] == 20 and status[0] == S.ONGOING and reps[0] == 1
+
+
+# ---- CPU: the product's shared rule code (csrc/chess.cuh is __host__ __device__) compiled for the host ------------------
+
+@pytest.fixture(scope="module")
+def host_rules(tmp_path_factory):
+    import ctypes as C
+    import shutil
+    import subprocess
+    if not shutil.which("nvcc"):
+        pytest.skip("nvcc not on PATH")
+    here = os.path.dirname(os.path.abspath(__file__))
+    out = str(tmp_path_factory.mktemp("chess_host") / "libchess_host.so")
+    subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O2", "-std=c++17", "--fmad=false", "-shared", "-Xcompiler", "-fPIC",
+                           "-o", out, os.path.join(here, "chess_host_check.cu")])
+    L = C.CDLL(out)
+    L.host_perft.restype = C.c_uint64
+    L.host_list_hash.restype = C.c_uint64
+    L.host_det_hash.restype = C.c_uint64
+    L.host_encode.restype = C.c_float
+    L.host_det_raw_prob.restype, L.host_det_raw_prob.argtypes = C.c_float, [C.c_uint64, C.c_int]
+    L.host_det_value.restype, L.host_det_value.argtypes = C.c_float, [C.c_uint64]
+    return L
+
+
+def test_shared_rule_code_matches_oracle_on_the_host(host_rules):
+    import ctypes as C
+    L = host_rules
+    buf = (C.c_uint16 * 256)()
+    for fen in P.PERFT:
+        s, _ = P.Game(fen).export()
+        assert L.host_perft(C.byref(s), 3) == P.PERFT[fen][2], fen
+    for g in random_games(12, seed=3, max_plies=150) + [P.Game(f) for f in P.PERFT if f]:
+        s, hist = g.export()
+        lm = g.legal_moves()
+        n = L.host_legal(C.byref(s), buf)
+        assert list(buf[:n]) == lm
+        assert L.host_det_hash(C.byref(s)) == P.det_hash(g)
+        for m in lm[:6]:
+            h = g.clone()
+            assert h.make_move(m) == 0 or g.status() != S.ONGOING
+            if g.status() == S.ONGOING:
+                out = P.ChessState()
+                L.host_apply(C.byref(s), m, C.byref(out))
+                want, wh = h.export()
+                out.hist_len = want.hist_len
+                assert bytes(out) == bytes(want), P.move_str(m)
+                arr = (C.c_uint16 * len(lm))(*lm)
+                assert L.host_list_hash(arr, len(lm)) == int(wh[want.hist_len - 1])
+        enc = g.encode()
+        reps = g.repetitions()
+        got = np.array([[[L.host_encode(C.byref(s), reps, p, r, c) for c in range(8)] for r in range(8)] for p in range(19)], np.float32)
+        assert np.array_equal(got, enc)
+        if not lm:
+            assert bool(L.host_in_check(C.byref(s))) == (g.status() == S.WON)      # mate vs stalemate
