@@ -6,6 +6,7 @@
 // cargo users.  Errors: where the reference returns Err(String) or panics, these functions throw spb::Error
 // (nothing crosses the C ABI as an exception).
 #pragma once
+#include <algorithm>
 #include <cstdint>
 #include <stdexcept>
 #include <string>
@@ -128,6 +129,95 @@ class Mcts {
   void check(int rc) { if (rc != SPB_OK) throw Error(rc, spb_last_error(e_)); }
   spb_engine* e_ = nullptr;
   int actions_ = 7;
+};
+
+// ---- chess (ref: src/game/chess.rs, src/model/chess.rs) ---------------------------------------------------------------
+// ref: chess::State {game, transposition_table, fifty_move_rule_halfmove_counter} (chess.rs:24-29): the position and, beside
+// it, one hash per ply of game history.  A move is from | to << 6 | promotion << 12.
+struct ChessState {
+  spb_chess_state raw{};
+  std::vector<uint64_t> history;                                                   // transposition_table as list hashes
+  int get_current_player() const { return raw.side; }                              // chess.rs:108-110
+  static ChessState start() { ChessState s; spb_chess_start_position(&s.raw); return s; }   // State::default(), chess.rs:94-102
+};
+
+class ChessTree {
+ public:
+  uint32_t slot;
+ private:
+  friend class ChessMcts;
+  explicit ChessTree(uint32_t s) : slot(s) {}
+};
+
+// ref: Mcts<chess Net>, mcts.rs:41-44 over model/chess.rs.
+class ChessMcts {
+ public:
+  Args args;
+  ChessMcts(const Args& a, int device = 0, int evaluator = SPB_EVAL_NET) : args(a) {
+    spb_config cfg;
+    spb_default_config(&cfg);
+    cfg.game = SPB_GAME_CHESS; cfg.device = device; cfg.evaluator = evaluator; cfg.c = a.c;
+    cfg.num_games = (uint32_t)a.num_parallel_self_play_games;
+    int rc = spb_chess_create(&cfg, &e_);
+    if (rc != SPB_OK) throw Error(rc, spb_chess_last_error(nullptr));
+  }
+  ~ChessMcts() { if (e_) spb_chess_destroy(e_); }
+  ChessMcts(const ChessMcts&) = delete;
+  ChessMcts& operator=(const ChessMcts&) = delete;
+
+  void load_weights(const std::vector<uint8_t>& safetensors) { check(spb_chess_load_weights(e_, safetensors.data(), safetensors.size())); }
+  // ref: Tree::with_root_state, mcts.rs:86
+  ChessTree with_root_state(uint32_t slot, const ChessState& s) {
+    std::vector<uint64_t> h(SPB_CHESS_MAX_HISTORY, 0);
+    for (size_t i = 0; i < s.history.size() && i < h.size(); ++i) h[i] = s.history[i];
+    spb_chess_state st = s.raw;
+    st.hist_len = (uint32_t)std::min<size_t>(s.history.size(), SPB_CHESS_MAX_HISTORY);
+    check(spb_chess_reset_games(e_, &slot, 1, &st, h.data()));
+    return ChessTree(slot);
+  }
+  // get_valid_actions / get_status (chess.rs:150-166) of one state
+  std::vector<uint16_t> get_valid_actions(const ChessState& s, Status* status = nullptr) {
+    std::vector<uint64_t> h(SPB_CHESS_MAX_HISTORY, 0);
+    for (size_t i = 0; i < s.history.size() && i < h.size(); ++i) h[i] = s.history[i];
+    std::vector<uint16_t> mv(SPB_CHESS_MAX_MOVES);
+    uint32_t n = 0; uint8_t st = 0;
+    spb_chess_state raw = s.raw;
+    raw.hist_len = (uint32_t)std::min<size_t>(s.history.size(), SPB_CHESS_MAX_HISTORY);
+    check(spb_chess_legal_moves(e_, &raw, h.data(), 1, mv.data(), &n, nullptr, &st, nullptr));
+    mv.resize(n);
+    if (status) *status = static_cast<Status>(st);
+    return mv;
+  }
+  uint64_t perft(const ChessState& s, uint32_t depth) { uint64_t n = 0; check(spb_chess_perft(e_, &s.raw, depth, &n)); return n; }
+  // ref: Mcts::search, mcts.rs:196-332: per tree [(child arena id, visit count)] with the children's moves.
+  struct Result { std::vector<uint16_t> moves; std::vector<std::pair<size_t, float>> child_id_to_probs; };
+  std::vector<Result> search(std::vector<ChessTree*>& trees) {
+    check(spb_chess_search(e_, args.num_searches));
+    std::vector<Result> out;
+    for (ChessTree* t : trees) {
+      std::vector<uint16_t> mv(SPB_CHESS_MAX_MOVES);
+      std::vector<uint32_t> cnt(SPB_CHESS_MAX_MOVES), ids(SPB_CHESS_MAX_MOVES);
+      uint32_t n = 0;
+      check(spb_chess_root_children(e_, t->slot, mv.data(), cnt.data(), ids.data(), &n));
+      Result r;
+      r.moves.assign(mv.begin(), mv.begin() + n);
+      for (uint32_t i = 0; i < n; ++i) r.child_id_to_probs.emplace_back(ids[i], (float)cnt[i]);
+      out.push_back(std::move(r));
+    }
+    return out;
+  }
+  // ref: Tree::use_subtree, mcts.rs:161-192 (a child of the root); returns the new root position.
+  spb_chess_state use_subtree(ChessTree& tree, size_t child_id) {
+    uint32_t id = (uint32_t)child_id;
+    spb_chess_state s{};
+    check(spb_chess_advance(e_, &tree.slot, &id, 1, &s));
+    return s;
+  }
+  size_t arena_len(const ChessTree& tree) { uint32_t n = 0; check(spb_chess_arena_len(e_, tree.slot, &n)); return n; }
+
+ private:
+  void check(int rc) { if (rc != SPB_OK) throw Error(rc, spb_chess_last_error(e_)); }
+  spb_chess_engine* e_ = nullptr;
 };
 
 }  // namespace spb

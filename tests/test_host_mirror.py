@@ -36,3 +36,27 @@ def test_host_mirror_plays_the_survey_greedy_game(exe):
     assert lines[1] == "status 2" and lines[2] == "error -1"
     arenas = [int(l.split()[-1]) for l in r.stderr.strip().splitlines()]
     assert arenas == KAT["c4_det_greedy_800"]["arena_sizes"]
+
+
+@pytest.mark.gpu
+def test_host_mirror_chess_perft_and_greedy_plies(exe):
+    """ChessMcts of the C++ mirror: device perft(3) of the start position, then four greedy DetEval plies with use_subtree
+    against the oracle's search."""
+    from oracle import pychess as P
+    r = subprocess.run([exe, "100", "chess"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    lines = r.stdout.strip().splitlines()
+    assert lines[0] == "perft3 8902 moves 20"
+    got = [int(x) for x in lines[1].split()[1:]]
+    f = P.Forest(1)
+    f.reset(0, P.Game())
+    want, arenas = [], []
+    for _ in range(4):
+        f.search(100, 1)
+        mvs, cnt, ids = f.root_children(0)
+        best = max(range(len(cnt)), key=lambda i: (cnt[i], i))
+        want.append(mvs[best])
+        arenas.append(f.arena_len(0))
+        f.use_subtree(0, ids[best])
+    assert got == want and lines[2] == "error -1"
+    assert [int(l.split()[-1]) for l in r.stderr.strip().splitlines()] == arenas
