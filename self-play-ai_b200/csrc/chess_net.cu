@@ -14,13 +14,16 @@
 //
 // k_conv<KC32, TAPS, N, EPI>: persistent CTAs, one 128-row M tile at a time, implicit GEMM M = 128, N = 256 (80 for the last
 // policy conv), K = TAPS x KC32 x 32:
-//   warp 0      producer: A tile (128 + 2 x 16 halo rows, all input channels, loaded ONCE and reused by the 9 taps; double
-//               buffered) and the weight stream (16 KB stages of 32 input channels x 256 outputs through a 4-deep ring),
-//               cp.async.bulk + mbarrier complete_tx
+//   warp 0      producer: A tile (128 + 2 x 16 halo rows, all input channels, loaded ONCE per tile and reused by the 9 taps)
+//               and the weight stream (16 KB stages of 32 input channels x 256 outputs through a 9-deep ring = 2,300
+//               cycles of cover for the L2 latency), cp.async.bulk + mbarrier complete_tx
 //   warp 1      MMA issuer: tcgen05.mma.cta_group::1.kind::f16 M = 128, N = 256, K = 16: 128 cycles each = the tensor
 //               pipe's rate, 144 per tile; accumulators in TMEM, 2 x 256 columns (double buffered)
 //   warps 2-5   epilogue: tcgen05.ld -> + bias (+ skip) -> ReLU -> bf16 -> HBM (pad rows forced to zero), or f32 logits
-// The epilogue of tile i and the A load of tile i+2 overlap the MMAs of tile i+1.
+// The K loop runs channel-group major (8 groups of 32 input channels, 9 taps each), so the A tile is 8 independent
+// sub-buffers: group g of the NEXT tile is loaded as soon as the 9 taps of group g of this tile have been read — the A
+// load is double-buffered at 1/8 granularity inside ONE 80 KB buffer, which leaves 144 KB for the weight ring.  The
+// epilogue of tile i overlaps the MMAs of tile i+1.
 // Algorithmic bytes per tile-layer: A 80 KB + weights 1,152 KB (L2-resident, 1.2 MB per layer) in, 64 KB out, against
 // 151 MFLOP: the kernel is tensor-bound (18.4 k cycles of MMA per tile) if L2 sustains 64 B/clk/SM of weight traffic.
 #include <cuda_bf16.h>
@@ -39,7 +42,7 @@ using namespace spb::umma;
 constexpr int BOARD_ROWS = 81;        // rows of one position
 constexpr int LEAD = 16;              // zero rows in front of the first position (taps reach back 10 rows)
 constexpr int QA = 160;               // rows of an A tile in shared memory: 16 halo + 128 + 16 halo
-constexpr int NSTAGE = 4;             // weight ring depth
+constexpr int NSTAGE = 9;             // weight ring depth
 constexpr int CONV_THREADS = 192;
 constexpr int IN_CHUNKS = 4;          // stem input: 19 planes padded to 32 channels
 
@@ -49,7 +52,7 @@ __host__ __device__ constexpr size_t plane_rows_for(uint32_t max_boards) { retur
 struct ConvArgs {
   const uint8_t* in;        // planar bf16 [KC32*4][plane_rows][8]
   uint8_t* out;             // planar bf16 [N/8][plane_rows][8] (EPI 0 / 1; EPI 1 adds the skip it reads from `out` itself)
-  const uint8_t* w;         // weight stages, [tap][kc32][4 chunks][N][8] bf16
+  const uint8_t* w;         // weight stages, [kc32][tap][4 chunks][N][8] bf16
   const float* bias;        // [N]
   const uint32_t* count;    // positions in this batch (device)
   uint32_t plane_rows;
@@ -64,10 +67,11 @@ struct ConvCfg {
   static constexpr int A_CHUNKS = KC32 * 4;
   static constexpr uint32_t A_BYTES = (uint32_t)A_CHUNKS * QA * 16;
   static constexpr uint32_t STAGE_BYTES = 4u * N * 16;
-  static constexpr uint32_t OFF_B = 2 * A_BYTES;
+  static constexpr uint32_t GROUP_BYTES = 4u * QA * 16;       // one 32-channel group of the A tile
+  static constexpr uint32_t OFF_B = A_BYTES;
   static constexpr uint32_t OFF_BIAS = OFF_B + NSTAGE * STAGE_BYTES;
   static constexpr uint32_t OFF_BAR = OFF_BIAS + 256 * 4;
-  static constexpr uint32_t SMEM = OFF_BAR + 32 * 8;
+  static constexpr uint32_t SMEM = OFF_BAR + 48 * 8;
 };
 
 template <int KC32, int TAPS, int N, int EPI>
@@ -77,19 +81,18 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv(const ConvArgs a) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bar0 = sbase + Cfg::OFF_BAR;
-  // barriers: a_full[2] a_empty[2] acc_full[2] acc_empty[2] b_full[NSTAGE] b_empty[NSTAGE], then the TMEM base word
-  const uint32_t A_FULL = bar0, A_EMPTY = bar0 + 16, ACC_FULL = bar0 + 32, ACC_EMPTY = bar0 + 48, B_FULL = bar0 + 64, B_EMPTY = bar0 + 64 + NSTAGE * 8;
-  uint32_t* tmem_word = reinterpret_cast<uint32_t*>(smem + Cfg::OFF_BAR + 30 * 8);
+  // barriers: a_full[8] a_empty[8] acc_full[2] acc_empty[2] b_full[NSTAGE] b_empty[NSTAGE], then the TMEM base word
+  const uint32_t A_FULL = bar0, A_EMPTY = bar0 + 64, ACC_FULL = bar0 + 128, ACC_EMPTY = bar0 + 144, B_FULL = bar0 + 160,
+                 B_EMPTY = bar0 + 160 + NSTAGE * 8;
+  uint32_t* tmem_word = reinterpret_cast<uint32_t*>(smem + Cfg::OFF_BAR + 46 * 8);
   float* s_bias = reinterpret_cast<float*>(smem + Cfg::OFF_BIAS);
 
   const uint32_t boards = *a.count;
   const uint32_t rows_used = boards * BOARD_ROWS;
   const uint32_t n_tiles = tiles_for(boards);
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(A_FULL + i * 8, 1); mbar_init(A_EMPTY + i * 8, 1);
-      mbar_init(ACC_FULL + i * 8, 1); mbar_init(ACC_EMPTY + i * 8, 4);
-    }
+    for (int i = 0; i < 8; ++i) { mbar_init(A_FULL + i * 8, 1); mbar_init(A_EMPTY + i * 8, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(ACC_FULL + i * 8, 1); mbar_init(ACC_EMPTY + i * 8, 4); }
     for (int i = 0; i < NSTAGE; ++i) { mbar_init(B_FULL + i * 8, 1); mbar_init(B_EMPTY + i * 8, 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -103,24 +106,25 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv(const ConvArgs a) {
   if (warp == 0) {
     // ---- producer ---------------------------------------------------------------------------------------------
     if (elect_one()) {
-      auto load_a = [&](uint32_t it, uint32_t tile) {
-        const uint32_t buf = it & 1u;
-        mbar_wait_sleep(A_EMPTY + buf * 8, ((it >> 1) & 1u) ^ 1u);
-        mbar_expect_tx(A_FULL + buf * 8, Cfg::A_BYTES);
-        const uint8_t* src = a.in + (size_t)tile * 128 * 16;      // rows [LEAD + 128 tile - 16, +160)
-#pragma unroll 4
-        for (int c = 0; c < Cfg::A_CHUNKS; ++c)
-          bulk_g2s(sbase + buf * Cfg::A_BYTES + (uint32_t)c * QA * 16, src + (size_t)c * a.plane_rows * 16, QA * 16, A_FULL + buf * 8);
-      };
       uint32_t it = 0, st = 0;
-      if (blockIdx.x < n_tiles) load_a(0, blockIdx.x);
       for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-        if (tile + gridDim.x < n_tiles) load_a(it + 1, tile + gridDim.x);
-        for (int s = 0; s < TAPS * KC32; ++s, ++st) {
-          const uint32_t slot = st % NSTAGE;
-          mbar_wait_sleep(B_EMPTY + slot * 8, ((st / NSTAGE) & 1u) ^ 1u);
-          mbar_expect_tx(B_FULL + slot * 8, Cfg::STAGE_BYTES);
-          bulk_g2s(sbase + Cfg::OFF_B + slot * Cfg::STAGE_BYTES, a.w + (size_t)s * Cfg::STAGE_BYTES, Cfg::STAGE_BYTES, B_FULL + slot * 8);
+        const uint8_t* src = a.in + (size_t)tile * 128 * 16;        // rows [LEAD + 128 tile - 16, +160) of every plane
+#pragma unroll 1
+        for (int kc = 0; kc < KC32; ++kc) {
+          // channel group kc of this tile's A: free once the 9 taps of the same group of the previous tile have been read
+          mbar_wait_sleep(A_EMPTY + kc * 8, (it & 1u) ^ 1u);
+          mbar_expect_tx(A_FULL + kc * 8, Cfg::GROUP_BYTES);
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            bulk_g2s(sbase + (uint32_t)(kc * 4 + c) * QA * 16, src + (size_t)(kc * 4 + c) * a.plane_rows * 16, QA * 16, A_FULL + kc * 8);
+#pragma unroll 1
+          for (int tap = 0; tap < TAPS; ++tap, ++st) {
+            const uint32_t slot = st % NSTAGE;
+            mbar_wait_sleep(B_EMPTY + slot * 8, ((st / NSTAGE) & 1u) ^ 1u);
+            mbar_expect_tx(B_FULL + slot * 8, Cfg::STAGE_BYTES);
+            bulk_g2s(sbase + Cfg::OFF_B + slot * Cfg::STAGE_BYTES, a.w + (size_t)(kc * TAPS + tap) * Cfg::STAGE_BYTES, Cfg::STAGE_BYTES,
+                     B_FULL + slot * 8);
+          }
         }
       }
     }
@@ -129,19 +133,20 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv(const ConvArgs a) {
     const bool issuer = elect_one();
     constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);          // SBO = 128 B, descriptor version 1
     constexpr uint32_t IDESC = make_idesc(N);
+    const uint32_t a_lo_base = ((sbase >> 4) + 16u) | ((uint32_t)QA << 16);   // row 16 of the buffer, LBO = QA rows
     uint32_t it = 0, st = 0;
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const uint32_t buf = it & 1u, par = (it >> 1) & 1u;
-      mbar_wait(A_FULL + buf * 8, par);
       mbar_wait(ACC_EMPTY + buf * 8, par ^ 1u);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + buf * 256;
-      const uint32_t a_lo_base = (((sbase + buf * Cfg::A_BYTES) >> 4) + 16u) | ((uint32_t)QA << 16);   // row 16 of the buffer, LBO = QA rows
 #pragma unroll 1
-      for (int tap = 0; tap < TAPS; ++tap) {
-        const int shift = TAPS == 9 ? (tap / 3 - 1) * 9 + (tap % 3 - 1) : 0;
+      for (int kc = 0; kc < KC32; ++kc) {
+        mbar_wait(A_FULL + kc * 8, it & 1u);
+        tc_fence_after();
 #pragma unroll 1
-        for (int kc = 0; kc < KC32; ++kc, ++st) {
+        for (int tap = 0; tap < TAPS; ++tap, ++st) {
+          const int shift = TAPS == 9 ? (tap / 3 - 1) * 9 + (tap % 3 - 1) : 0;
           const uint32_t slot = st % NSTAGE;
           mbar_wait(B_FULL + slot * 8, (st / NSTAGE) & 1u);
           tc_fence_after();
@@ -157,11 +162,10 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv(const ConvArgs a) {
           }
           __syncwarp();
         }
+        if (issuer) umma_commit(A_EMPTY + kc * 8);                  // this channel group of the A tile has been read
+        __syncwarp();
       }
-      if (issuer) {
-        umma_commit(ACC_FULL + buf * 8);
-        umma_commit(A_EMPTY + buf * 8);
-      }
+      if (issuer) umma_commit(ACC_FULL + buf * 8);
       __syncwarp();
     }
   } else {
@@ -325,12 +329,12 @@ static inline uint16_t f2bf(float f) {
   return (uint16_t)(u >> 16);
 }
 
-// weight stages of one conv: [tap][kc32][4 chunks][N][8] bf16; input channels padded to kc32*32, outputs to N
+// weight stages of one conv: [kc32][tap][4 chunks][N][8] bf16; input channels padded to kc32*32, outputs to N
 static void pack_conv(const HostNet::Conv& cv, int kc32, int N, uint16_t* dst) {
   const int taps = cv.k * cv.k;
   for (int tap = 0; tap < taps; ++tap)
     for (int kc = 0; kc < kc32; ++kc) {
-      uint16_t* st = dst + ((size_t)tap * kc32 + kc) * 4 * N * 8;
+      uint16_t* st = dst + ((size_t)kc * taps + tap) * 4 * N * 8;
       for (int n = 0; n < N; ++n)
         for (int kl = 0; kl < 32; ++kl) {
           const int k = kc * 32 + kl;
