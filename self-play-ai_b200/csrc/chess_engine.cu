@@ -181,6 +181,9 @@ __global__ void __launch_bounds__(THREADS) k_chess_select(CTrees T) {
 // softmax over all 4,672 logits, then mask_invalid_actions = keep the legal cells and divide by their sum
 // (chess.rs:251-271).  The normaliser of the softmax cancels in that division, so only the legal logits are read:
 // prior_i = exp(l_i - m) / sum_legal exp(l_j - m), m = max over the legal logits.
+// RAW = true (parity harness, SPB_FLAG_FORCE_SPLIT): eval_logits holds the raw probabilities of a built-in evaluator for the
+// legal cells (k_chess_builtin_eval) and the prior is raw / sum, exactly as in the fused kernel.
+template <bool RAW>
 __global__ void __launch_bounds__(THREADS) k_chess_finish(CTrees T) {
   __shared__ WarpScratch s_ws[WARPS];
   __shared__ float s_e[WARPS][MAX_MOVES];
@@ -212,9 +215,9 @@ __global__ void __launch_bounds__(THREADS) k_chess_finish(CTrees T) {
   for (int o = 16; o >= 1; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   float sum = 0.0f;
   for (int i = lane; i < n; i += 32) {
-    const float e = __expf(s_e[w][i] - mx);
+    const float e = RAW ? s_e[w][i] : __expf(s_e[w][i] - mx);
     s_e[w][i] = e;
-    sum += e;
+    sum += e;                                                        // RAW: dyadic values, exact in any order
   }
 #pragma unroll
   for (int o = 16; o >= 1; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
@@ -233,6 +236,25 @@ __global__ void __launch_bounds__(THREADS) k_chess_finish(CTrees T) {
   }
   __syncwarp();
   backup(rec, ws, depth, T.eval_value[g], lane);
+}
+
+// Built-in evaluators for the lock-step pipeline (parity harness): the raw probabilities of the legal cells and the value of
+// every pending leaf, where the network would have written its logits.
+template <int EVAL>
+__global__ void __launch_bounds__(THREADS) k_chess_builtin_eval(CTrees T) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t i = blockIdx.x * WARPS + (threadIdx.x >> 5);
+  if (i >= *T.eval_count) return;
+  const uint32_t g = T.eval_list[i];
+  const Pos pos = T.leaf_pos[g];
+  const uint64_t dh = det_hash(pos);
+  const int n = (int)T.leaf_nmoves[g];
+  float* logits = T.eval_logits + (size_t)g * LOGIT_STRIDE;
+  for (int k = lane; k < n; k += 32) {
+    const int idx = policy_index(pos.side, T.leaf_moves[(size_t)g * MAX_MOVES + k]);
+    logits[idx] = EVAL == SPB_EVAL_DET ? det_raw_prob(dh, idx) : 1.0f;
+  }
+  if (lane == 0) T.eval_value[g] = EVAL == SPB_EVAL_DET ? det_value(dh) : 0.0f;
 }
 
 // ---- results / re-rooting ----------------------------------------------------------------------------------------
@@ -441,7 +463,7 @@ int32_t spb_chess_create(const spb_config* cfg, spb_chess_engine** out) {
   if (!rc) rc = e->dalloc(&T.eval_list, G);
   if (!rc) rc = e->dalloc(&T.eval_count, 1);
   if (!rc) rc = e->dalloc(&T.eval_value, G);
-  if (!rc && cfg->evaluator == SPB_EVAL_NET) rc = e->dalloc(&T.eval_logits, G * (size_t)ch::LOGIT_STRIDE);
+  if (!rc && (cfg->evaluator == SPB_EVAL_NET || (cfg->flags & SPB_FLAG_FORCE_SPLIT))) rc = e->dalloc(&T.eval_logits, G * (size_t)ch::LOGIT_STRIDE);
   if (!rc) rc = e->dalloc(&e->d_rc_moves, G * ch::MAX_MOVES);
   if (!rc) rc = e->dalloc(&e->d_rc_counts, G * ch::MAX_MOVES);
   if (!rc) rc = e->dalloc(&e->d_rc_ids, G * ch::MAX_MOVES);
@@ -517,9 +539,20 @@ int32_t spb_chess_search(spb_chess_engine* e, uint32_t num_searches) {
       uint32_t launched = 0;
       const int32_t rc = ch::net_forward_leaves(e, &launched);
       if (rc) return rc;
-      ch::k_chess_finish<<<blocks, ch::THREADS, 0, e->stream>>>(e->T);
+      ch::k_chess_finish<false><<<blocks, ch::THREADS, 0, e->stream>>>(e->T);
       CH_CUDA(e, cudaGetLastError());
       e->launches += 2 + launched;
+    }
+  } else if (e->cfg.flags & SPB_FLAG_FORCE_SPLIT) {
+    // parity harness: the built-in evaluators through the kernels of the network pipeline (select -> evaluate -> finish)
+    for (uint32_t s = 0; s < num_searches; ++s) {
+      CH_CUDA(e, cudaMemsetAsync(e->T.eval_count, 0, 4, e->stream));
+      ch::k_chess_select<<<blocks, ch::THREADS, 0, e->stream>>>(e->T);
+      if (e->cfg.evaluator == SPB_EVAL_DET) ch::k_chess_builtin_eval<SPB_EVAL_DET><<<blocks, ch::THREADS, 0, e->stream>>>(e->T);
+      else ch::k_chess_builtin_eval<SPB_EVAL_UNIFORM><<<blocks, ch::THREADS, 0, e->stream>>>(e->T);
+      ch::k_chess_finish<true><<<blocks, ch::THREADS, 0, e->stream>>>(e->T);
+      CH_CUDA(e, cudaGetLastError());
+      e->launches += 3;
     }
   } else {
     if (e->cfg.evaluator == SPB_EVAL_DET) ch::k_chess_search_fused<SPB_EVAL_DET><<<blocks, ch::THREADS, 0, e->stream>>>(e->T, num_searches);

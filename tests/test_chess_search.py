@@ -394,3 +394,78 @@ def test_chess_network_search_matches_oracle_with_torch_evaluator(chess_net):
             pri_ref = np.array([f.node(i, fc + k)["prior"] for k in range(len(mvs))])
             pri = np.array([e.node_stats(i, fc + k)["prior"] for k in range(len(mvs))])
             assert np.allclose(pri, pri_ref, rtol=5 * RTOL, atol=1e-4), i
+
+
+# ---- GPU: the kernels of the network pipeline under the deterministic evaluators, and the full size of configs[4] --------
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("evaluator", [S.EVAL_DET, S.EVAL_UNIFORM])
+def test_device_lockstep_pipeline_matches_oracle_node_for_node(evaluator):
+    """SPB_FLAG_FORCE_SPLIT: select -> evaluate -> expand + backup as three kernels per simulation step (the pipeline the
+    network uses) instead of the fused kernel; results must not change by a bit."""
+    games = search_roots()
+    st, hist = export_all(games)
+    f = oracle_forest(games, 150, evaluator)
+    with S.ChessEngine(num_games=len(games), evaluator=evaluator, flags=S.FLAG_FORCE_SPLIT) as e:
+        e.reset_games(st, hist)
+        e.search(150)
+        for i in range(len(games)):
+            assert e.root_children(i) == f.root_children(i), i
+        for i in (0, 2, 4, len(games) - 1):
+            assert tree_table_device(e, i) == tree_table_oracle(f, i), i
+        c, want = e.counters(), f.counters()
+        for k in want:
+            assert c[k] == want[k], k
+
+
+def synthetic_chess_root(g, max_ply=41):
+    """The oracle-side twin of selfplay_b200.synth.synthetic_chess_roots_device (bench.py --game chess)."""
+    from helpers import splitmix64
+    while True:
+        r = splitmix64(0xC4E55000 + g)
+        plies = r % max_ply
+        game = P.Game()
+        ok = True
+        for _ in range(plies):
+            if game.status() != 0:
+                ok = False
+                break
+            lm = game.legal_moves()
+            r = splitmix64(r)
+            game.make_move(lm[r % len(lm)])
+        if ok and game.status() == 0:
+            return game
+        g += 1 << 32
+
+
+@pytest.mark.gpu
+def test_full_size_chess_4096_games_x_200_sims():
+    """configs[4] at full size under DetEval: the bench's synthetic roots come out of the device rules exactly as the oracle
+    builds them; 4,096 trees x 200 simulations; 12 trees spread over the batch replayed by the oracle node for node; every
+    tree conserves its budget; fused and lock-step pipelines agree on every root (SHA-256)."""
+    import hashlib
+    from selfplay_b200.synth import synthetic_chess_roots_device
+    G, sims = 4096, 200
+    digests = []
+    for flags in (0, S.FLAG_FORCE_SPLIT):
+        with S.ChessEngine(num_games=G, evaluator=S.EVAL_DET, flags=flags, max_nodes_per_tree=14336) as e:
+            st, hist = synthetic_chess_roots_device(e, G)
+            sample = list(range(0, G, 372))
+            if flags == 0:
+                for i in sample:
+                    ws, wh = synthetic_chess_root(i).export()
+                    assert st[i].tobytes() == bytes(ws) and (hist[i] == wh).all(), i
+            e.reset_games(st, hist)
+            e.search(sims)
+            mv, cnt, ids, n = e.root_children_all()
+            assert (cnt.sum(1) == sims - 1).all() and (n > 0).all()
+            c = e.counters()
+            assert c["simulations"] == G * sims and c["evaluations"] + c["terminal_leaves"] == G * sims
+            digests.append(hashlib.sha256(mv.tobytes() + cnt.tobytes() + ids.tobytes() + n.tobytes()).hexdigest())
+            if flags == 0:
+                games = [synthetic_chess_root(i) for i in sample]
+                f = oracle_forest(games, sims, S.EVAL_DET)
+                for k, i in enumerate(sample):
+                    assert e.root_children(i) == f.root_children(k), i
+                    assert e.arena_len(i) == f.arena_len(k), i
+    assert digests[0] == digests[1]
