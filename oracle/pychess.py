@@ -84,8 +84,11 @@ class Game:
             raise ValueError("bad FEN")
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            _lib().orc_chess_free(self._h)
+        if getattr(self, "_h", None) and _lib is not None:           # module globals are gone at interpreter shutdown
+            try:
+                _lib().orc_chess_free(self._h)
+            except Exception:
+                pass
             self._h = None
 
     def clone(self):
@@ -135,8 +138,11 @@ class Forest:
         self.n = n
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            _lib().orc_chess_forest_free(self._h)
+        if getattr(self, "_h", None) and _lib is not None:
+            try:
+                _lib().orc_chess_forest_free(self._h)
+            except Exception:
+                pass
             self._h = None
 
     def reset(self, slot: int, game: "Game"):

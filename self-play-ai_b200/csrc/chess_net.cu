@@ -12,20 +12,23 @@
 // memory as the K-major no-swizzle UMMA operand layout (8-row core matrices of 128 contiguous bytes at ANY row offset, so a
 // tap shift is just the descriptor's start address: verified by tools/umma_probe.cu).
 //
-// k_conv<KC32, TAPS, N, EPI>: persistent CTAs, one 128-row M tile at a time, implicit GEMM M = 128, N = 256 (80 for the last
-// policy conv), K = TAPS x KC32 x 32:
-//   warp 0      producer: A tile (128 + 2 x 16 halo rows, all input channels, loaded ONCE per tile and reused by the 9 taps)
-//               and the weight stream (16 KB stages of 32 input channels x 256 outputs through a 9-deep ring = 2,300
+// k_conv<KC32, TAPS, N, EPI>: persistent CTAs, one M tile at a time, implicit GEMM M = 128, N = 256 (80 for the last policy
+// conv), K = TAPS x KC32 x 32.  An M tile is 16 board rows of 8 cells: the A descriptor strides 9 layout rows (144 B) between
+// its 8-row core matrices, so the zero pad column never enters the MMA (8/9 of the tile rows are real cells).
+//   warp 0      producer: A tile (169 layout rows incl. halo, all input channels, loaded ONCE per tile and reused by the 9
+//               taps) and the weight stream (16 KB stages of 32 input channels x 256 outputs through an 8-deep ring = 2,000
 //               cycles of cover for the L2 latency), cp.async.bulk + mbarrier complete_tx
 //   warp 1      MMA issuer: tcgen05.mma.cta_group::1.kind::f16 M = 128, N = 256, K = 16: 128 cycles each = the tensor
 //               pipe's rate, 144 per tile; accumulators in TMEM, 2 x 256 columns (double buffered)
-//   warps 2-5   epilogue: tcgen05.ld -> + bias (+ skip) -> ReLU -> bf16 -> HBM (pad rows forced to zero), or f32 logits
+//   warps 2-5   epilogue: tcgen05.ld -> + bias (+ skip) -> ReLU -> bf16 -> HBM, or f32 logits; pad cells are never written
+//               (they are zero from the allocation on and supply the conv's zero padding)
 // The K loop runs channel-group major (8 groups of 32 input channels, 9 taps each), so the A tile is 8 independent
 // sub-buffers: group g of the NEXT tile is loaded as soon as the 9 taps of group g of this tile have been read — the A
-// load is double-buffered at 1/8 granularity inside ONE 80 KB buffer, which leaves 144 KB for the weight ring.  The
+// load is double-buffered at 1/8 granularity inside ONE 85 KB buffer, which leaves 128 KB for the weight ring.  The
 // epilogue of tile i overlaps the MMAs of tile i+1.
-// Algorithmic bytes per tile-layer: A 80 KB + weights 1,152 KB (L2-resident, 1.2 MB per layer) in, 64 KB out, against
-// 151 MFLOP: the kernel is tensor-bound (18.4 k cycles of MMA per tile) if L2 sustains 64 B/clk/SM of weight traffic.
+// Algorithmic bytes per tile-layer: A 85 KB + weights 1,152 KB (L2-resident, 1.2 MB per layer) in, 57 KB out, against
+// 134 MFLOP of real cells (151 MFLOP issued): the kernel is tensor-bound (18.4 k cycles of MMA per tile) as long as L2
+// sustains 64 B/clk/SM of weight traffic.
 #include <cuda_bf16.h>
 
 #include <cstring>
@@ -39,15 +42,20 @@ namespace chess {
 
 using namespace spb::umma;
 
-constexpr int BOARD_ROWS = 81;        // rows of one position
+constexpr int BOARD_ROWS = 81;        // layout rows of one position: 9 board rows (8 + the shared zero row) x 9 cells (8 + the zero column)
 constexpr int LEAD = 16;              // zero rows in front of the first position (taps reach back 10 rows)
-constexpr int QA = 160;               // rows of an A tile in shared memory: 16 halo + 128 + 16 halo
-constexpr int NSTAGE = 9;             // weight ring depth
+// An M tile is 16 BOARD ROWS of 8 real cells: the A descriptor's stride between 8-row core matrices (SBO) is 9 layout rows
+// (144 bytes), so the zero pad COLUMN never enters the MMA — 8 of every 9 tile rows are real cells (the 9th board row of a
+// position, its zero pad row, still does): 89 % useful rows instead of 79 % with 128 consecutive layout rows per tile.
+constexpr int TILE_BROWS = 16;                    // board rows per tile
+constexpr int TILE_SPAN = TILE_BROWS * 9;         // layout rows one tile spans: 144
+constexpr int QA = 16 + (TILE_BROWS - 1) * 9 + 8 + 10;   // rows of an A tile in shared memory: 16 halo + 143 + 10 halo = 169
+constexpr int NSTAGE = 8;             // weight ring depth
 constexpr int CONV_THREADS = 192;
 constexpr int IN_CHUNKS = 4;          // stem input: 19 planes padded to 32 channels
 
-__host__ __device__ constexpr uint32_t tiles_for(uint32_t boards) { return (boards * BOARD_ROWS + 127u) / 128u; }
-__host__ __device__ constexpr size_t plane_rows_for(uint32_t max_boards) { return (size_t)LEAD + (size_t)tiles_for(max_boards) * 128 + 32; }
+__host__ __device__ constexpr uint32_t tiles_for(uint32_t boards) { return (boards * 9u + TILE_BROWS - 1u) / TILE_BROWS; }
+__host__ __device__ constexpr size_t plane_rows_for(uint32_t max_boards) { return (size_t)LEAD + (size_t)tiles_for(max_boards) * TILE_SPAN + 64; }
 
 struct ConvArgs {
   const uint8_t* in;        // planar bf16 [KC32*4][plane_rows][8]
@@ -88,7 +96,6 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv(const ConvArgs a) {
   float* s_bias = reinterpret_cast<float*>(smem + Cfg::OFF_BIAS);
 
   const uint32_t boards = *a.count;
-  const uint32_t rows_used = boards * BOARD_ROWS;
   const uint32_t n_tiles = tiles_for(boards);
   if (threadIdx.x == 0) {
     for (int i = 0; i < 8; ++i) { mbar_init(A_FULL + i * 8, 1); mbar_init(A_EMPTY + i * 8, 1); }
@@ -108,7 +115,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv(const ConvArgs a) {
     if (elect_one()) {
       uint32_t it = 0, st = 0;
       for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-        const uint8_t* src = a.in + (size_t)tile * 128 * 16;        // rows [LEAD + 128 tile - 16, +160) of every plane
+        const uint8_t* src = a.in + (size_t)tile * TILE_SPAN * 16;  // rows [LEAD + 144 tile - 16, + QA) of every plane
 #pragma unroll 1
         for (int kc = 0; kc < KC32; ++kc) {
           // channel group kc of this tile's A: free once the 9 taps of the same group of the previous tile have been read
@@ -131,7 +138,8 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv(const ConvArgs a) {
   } else if (warp == 1) {
     // ---- MMA issuer -------------------------------------------------------------------------------------------
     const bool issuer = elect_one();
-    constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);          // SBO = 128 B, descriptor version 1
+    constexpr uint32_t DESC_HI_A = 9u | (1u << 14);                 // A: SBO = 9 rows = 144 B between core matrices, descriptor version 1
+    constexpr uint32_t DESC_HI_B = (128u >> 4) | (1u << 14);        // B: SBO = 128 B
     constexpr uint32_t IDESC = make_idesc(N);
     const uint32_t a_lo_base = ((sbase >> 4) + 16u) | ((uint32_t)QA << 16);   // row 16 of the buffer, LBO = QA rows
     uint32_t it = 0, st = 0;
@@ -156,7 +164,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv(const ConvArgs a) {
             for (int kk = 0; kk < 2; ++kk) {
               const uint32_t a_lo = a_lo_base + (uint32_t)(shift + (kc * 4 + kk * 2) * QA);
               const uint32_t b_lo = b_lo_base + (uint32_t)(kk * 2 * N);
-              umma_f16(d_tmem, ((uint64_t)DESC_HI << 32) | a_lo, ((uint64_t)DESC_HI << 32) | b_lo, IDESC, (tap | kc | kk) != 0);
+              umma_f16(d_tmem, ((uint64_t)DESC_HI_A << 32) | a_lo, ((uint64_t)DESC_HI_B << 32) | b_lo, IDESC, (tap | kc | kk) != 0);
             }
             umma_commit(B_EMPTY + slot * 8);
           }
@@ -176,13 +184,15 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv(const ConvArgs a) {
       const uint32_t buf = it & 1u, par = (it >> 1) & 1u;
       mbar_wait(ACC_FULL + buf * 8, par);
       tc_fence_after();
-      const uint32_t r_global = tile * 128 + (uint32_t)(q * 32 + lane);
-      const uint32_t board = r_global / BOARD_ROWS, cell = r_global % BOARD_ROWS;
-      const bool pad = r_global >= rows_used || cell % 9 == 8 || cell / 9 == 8;
+      // TMEM lane r = board row (r >> 3) of the tile, cell (r & 7)
+      const uint32_t brow = tile * TILE_BROWS + (uint32_t)((q * 32 + lane) >> 3), x = (uint32_t)(lane & 7);
+      const uint32_t board = brow / 9u, y = brow % 9u;
+      const bool pad = y == 8u || board >= boards;                    // the shared zero row / beyond the batch: never written
+      const uint32_t r_layout = brow * 9u + x;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 256;
       if (EPI == EPI_LOGITS) {
         const uint32_t slot = (!pad && a.list) ? a.list[board] : board;
-        float* dst = a.logits + (size_t)slot * SPB_CHESS_POLICY_SIZE + (cell / 9) * 8 + (cell % 9);
+        float* dst = a.logits + (size_t)slot * SPB_CHESS_POLICY_SIZE + y * 8 + x;
 #pragma unroll 1
         for (int c16 = 0; c16 < N / 16; ++c16) {
           uint32_t r[16];
@@ -197,36 +207,37 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv(const ConvArgs a) {
           }
         }
       } else {
-        uint8_t* orow = a.out + ((size_t)LEAD + r_global) * 16;
+        uint8_t* orow = a.out + ((size_t)LEAD + r_layout) * 16;
 #pragma unroll 1
         for (int c32 = 0; c32 < N / 32; ++c32) {
           uint32_t r[32];
           tmem_ld16(taddr + c32 * 32, r);
           tmem_ld16(taddr + c32 * 32 + 16, r + 16);
           uint4 sk[4];
-          if (EPI == EPI_SKIP_RELU) {
+          if (EPI == EPI_SKIP_RELU && !pad) {
 #pragma unroll
             for (int c = 0; c < 4; ++c) sk[c] = *reinterpret_cast<const uint4*>(orow + (size_t)(c32 * 4 + c) * a.plane_rows * 16);
           }
           tmem_ld_wait();
+          if (!pad) {
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const int ch0 = c32 * 32 + c * 8;
-            float v[8];
+            for (int c = 0; c < 4; ++c) {
+              const int ch0 = c32 * 32 + c * 8;
+              float v[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[c * 8 + j]) + s_bias[ch0 + j];
-            if (EPI == EPI_SKIP_RELU) {
-              const uint32_t s4[4] = {sk[c].x, sk[c].y, sk[c].z, sk[c].w};
+              for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[c * 8 + j]) + s_bias[ch0 + j];
+              if (EPI == EPI_SKIP_RELU) {
+                const uint32_t s4[4] = {sk[c].x, sk[c].y, sk[c].z, sk[c].w};
 #pragma unroll
-              for (int j = 0; j < 4; ++j) { v[2 * j] += bf_lo(s4[j]); v[2 * j + 1] += bf_hi(s4[j]); }
+                for (int j = 0; j < 4; ++j) { v[2 * j] += bf_lo(s4[j]); v[2 * j + 1] += bf_hi(s4[j]); }
+              }
+              uint4 o;
+              o.x = pack_bf16x2(fmaxf(v[0], 0.f), fmaxf(v[1], 0.f));
+              o.y = pack_bf16x2(fmaxf(v[2], 0.f), fmaxf(v[3], 0.f));
+              o.z = pack_bf16x2(fmaxf(v[4], 0.f), fmaxf(v[5], 0.f));
+              o.w = pack_bf16x2(fmaxf(v[6], 0.f), fmaxf(v[7], 0.f));
+              *reinterpret_cast<uint4*>(orow + (size_t)(c32 * 4 + c) * a.plane_rows * 16) = o;
             }
-            uint4 o;
-            o.x = pack_bf16x2(fmaxf(v[0], 0.f), fmaxf(v[1], 0.f));
-            o.y = pack_bf16x2(fmaxf(v[2], 0.f), fmaxf(v[3], 0.f));
-            o.z = pack_bf16x2(fmaxf(v[4], 0.f), fmaxf(v[5], 0.f));
-            o.w = pack_bf16x2(fmaxf(v[6], 0.f), fmaxf(v[7], 0.f));
-            if (pad) o = make_uint4(0u, 0u, 0u, 0u);
-            *reinterpret_cast<uint4*>(orow + (size_t)(c32 * 4 + c) * a.plane_rows * 16) = o;
           }
         }
       }
@@ -244,7 +255,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv(const ConvArgs a) {
 __global__ void k_encode_input(const Pos* pos, const uint32_t* reps, const uint32_t* list, const uint32_t* count, uint8_t* out, uint32_t plane_rows) {
   const uint32_t boards = *count;
   const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;          // row of the batch
-  const uint32_t n_rows = tiles_for(boards) * 128;
+  const uint32_t n_rows = tiles_for(boards) * TILE_SPAN;
   if (r >= n_rows) return;
   const uint32_t board = r / BOARD_ROWS, cell = r % BOARD_ROWS, row = cell / 9, col = cell % 9;
   float v[32];
@@ -292,7 +303,7 @@ __global__ void __launch_bounds__(256) k_value_head(const uint8_t* x, uint32_t p
   if (t < 64) s_cell[t] = fmaxf(s_part[0][t] + s_part[1][t] + s_part[2][t] + s_part[3][t] + vconv_b[0], 0.0f);
   __syncthreads();
   float h = fc1_b[t];
-  for (int k = 0; k < 64; ++k) h += fc1_w[t * 64 + k] * s_cell[k];
+  for (int k = 0; k < 64; ++k) h += fc1_w[k * 256 + t] * s_cell[k];   // fc1_w is stored transposed [64][256]: coalesced over t
   float y = fmaxf(h, 0.0f) * fc2_w[t];
 #pragma unroll
   for (int o = 16; o >= 1; o >>= 1) y += __shfl_xor_sync(0xffffffffu, y, o);
@@ -406,7 +417,8 @@ bool net_upload(Net* net, const HostNet& h, std::string* err) {
   std::copy(h.p2.b.begin(), h.p2.b.end(), f.begin() + net->off_bp2);
   std::copy(h.vconv.w.begin(), h.vconv.w.end(), f.begin() + net->off_vw);
   f[net->off_vb] = h.vconv.b[0];
-  std::copy(h.fc1_w.begin(), h.fc1_w.end(), f.begin() + net->off_f1w);
+  for (int o = 0; o < 256; ++o)
+    for (int k = 0; k < 64; ++k) f[net->off_f1w + (size_t)k * 256 + o] = h.fc1_w[(size_t)o * 64 + k];   // transposed for the value-head kernel
   std::copy(h.fc1_b.begin(), h.fc1_b.end(), f.begin() + net->off_f1b);
   std::copy(h.fc2_w.begin(), h.fc2_w.end(), f.begin() + net->off_f2w);
   f[net->off_f2b] = h.fc2_b[0];
@@ -439,7 +451,7 @@ static cudaError_t launch_conv(Net* net, const ConvArgs& a, cudaStream_t stream)
 cudaError_t net_forward(Net* net, const Pos* pos, const uint32_t* reps, const uint32_t* list, const uint32_t* count_dev, float* logits,
                         float* values, cudaStream_t stream, uint32_t* launched) {
   const uint32_t plane_rows = (uint32_t)net->plane_rows;
-  const uint32_t max_rows = tiles_for(net->max_positions) * 128;
+  const uint32_t max_rows = tiles_for(net->max_positions) * TILE_SPAN;
   uint32_t n = 0;
   cudaError_t e;
   k_encode_input<<<(max_rows + 127) / 128, 128, 0, stream>>>(pos, reps, list, count_dev, net->d_in, plane_rows);
@@ -603,7 +615,7 @@ int32_t spb_chess_time_conv(spb_chess_engine* e, uint32_t iters, float* avg_ms, 
   if (ce != cudaSuccess) { e->set_error(std::string("chess conv timing: ") + cudaGetErrorString(ce)); return SPB_ERR_CUDA; }
   e->launches += iters + 1;
   *n_positions = n;
-  *flops_per_launch = (double)n * 2.0 * 64 * 256 * 9 * 256;
+  *flops_per_launch = (double)n * 2.0 * 64 * 256 * 9 * 256;           // algorithmic: the 64 real cells of a position
   *flops_per_position = ch::net_flops_per_position();
   return SPB_OK;
 }
