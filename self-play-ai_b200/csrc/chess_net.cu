@@ -17,7 +17,8 @@
 // its 8-row core matrices, so the zero pad column never enters the MMA (8/9 of the tile rows are real cells).
 //   warp 0      producer: A tile (169 layout rows incl. halo, all input channels, loaded ONCE per tile and reused by the 9
 //               taps) and the weight stream (16 KB stages of 32 input channels x 256 outputs through an 8-deep ring = 2,000
-//               cycles of cover for the L2 latency), cp.async.bulk + mbarrier complete_tx
+//               cycles of cover for the L2 latency), cp.async.bulk + mbarrier complete_tx.  CTAs run in PAIRS (clusters of
+//               2) on different tiles with the same weights: each loads half of every stage and multicasts it to both.
 //   warp 1      MMA issuer: tcgen05.mma.cta_group::1.kind::f16 M = 128, N = 256, K = 16: 128 cycles each = the tensor
 //               pipe's rate, 144 per tile; accumulators in TMEM, 2 x 256 columns (double buffered)
 //   warps 2-5   epilogue: tcgen05.ld -> + bias (+ skip) -> ReLU -> bf16 -> HBM, or f32 logits; pad cells are never written
@@ -55,7 +56,24 @@ constexpr int CONV_THREADS = 192;
 constexpr int IN_CHUNKS = 4;          // stem input: 19 planes padded to 32 channels
 
 __host__ __device__ constexpr uint32_t tiles_for(uint32_t boards) { return (boards * 9u + TILE_BROWS - 1u) / TILE_BROWS; }
-__host__ __device__ constexpr size_t plane_rows_for(uint32_t max_boards) { return (size_t)LEAD + (size_t)tiles_for(max_boards) * TILE_SPAN + 64; }
+// + one tile: the second CTA of a pair runs a dummy tile when the number of tiles is odd
+__host__ __device__ constexpr size_t plane_rows_for(uint32_t max_boards) { return (size_t)LEAD + (size_t)(tiles_for(max_boards) + 1) * TILE_SPAN + 64; }
+
+// ---- CTA pairs: the two CTAs of a cluster work on different M tiles with the SAME weights, so each loads half of every
+// weight stage and multicasts it into both shared memories (L2 weight traffic halves); a stage is refilled when the MMAs of
+// BOTH CTAs have read it (tcgen05.commit multicast to both CTAs' "empty" barriers).
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_g2s_multicast(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void umma_commit_multicast(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
+}
 
 struct ConvArgs {
   const uint8_t* in;        // planar bf16 [KC32*4][plane_rows][8]
@@ -83,7 +101,7 @@ struct ConvCfg {
 };
 
 template <int KC32, int TAPS, int N, int EPI>
-__global__ void __launch_bounds__(CONV_THREADS, 1) k_conv(const ConvArgs a) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) k_conv(const ConvArgs a) {
   using Cfg = ConvCfg<KC32, TAPS, N, EPI>;
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -97,16 +115,21 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv(const ConvArgs a) {
 
   const uint32_t boards = *a.count;
   const uint32_t n_tiles = tiles_for(boards);
+  // pair p of the grid's CTA pairs takes tiles 2p and 2p+1 (an odd tail leaves one CTA a dummy tile beyond the batch: its
+  // rows are allocated, its epilogue writes nothing), so both CTAs of a pair always run the same number of weight stages
+  const uint32_t rank = cluster_ctarank();
+  const uint32_t pair0 = blockIdx.x >> 1, n_pairs_grid = gridDim.x >> 1, n_pair_tiles = (n_tiles + 1u) >> 1;
   if (threadIdx.x == 0) {
     for (int i = 0; i < 8; ++i) { mbar_init(A_FULL + i * 8, 1); mbar_init(A_EMPTY + i * 8, 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(ACC_FULL + i * 8, 1); mbar_init(ACC_EMPTY + i * 8, 4); }
-    for (int i = 0; i < NSTAGE; ++i) { mbar_init(B_FULL + i * 8, 1); mbar_init(B_EMPTY + i * 8, 1); }
+    for (int i = 0; i < NSTAGE; ++i) { mbar_init(B_FULL + i * 8, 1); mbar_init(B_EMPTY + i * 8, 2); }   // empty: both CTAs' MMAs
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int i = threadIdx.x; i < N; i += CONV_THREADS) s_bias[i] = a.bias[i];
   if (warp == 1) tmem_alloc(smem_u32(tmem_word), 512);
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();                                                // the peer's barriers exist before anything is sent to them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_word;
 
@@ -114,7 +137,9 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv(const ConvArgs a) {
     // ---- producer ---------------------------------------------------------------------------------------------
     if (elect_one()) {
       uint32_t it = 0, st = 0;
-      for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      constexpr uint32_t HALF = Cfg::STAGE_BYTES / 2;
+      for (uint32_t pt = pair0; pt < n_pair_tiles; pt += n_pairs_grid, ++it) {
+        const uint32_t tile = 2u * pt + rank;
         const uint8_t* src = a.in + (size_t)tile * TILE_SPAN * 16;  // rows [LEAD + 144 tile - 16, + QA) of every plane
 #pragma unroll 1
         for (int kc = 0; kc < KC32; ++kc) {
@@ -127,12 +152,17 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv(const ConvArgs a) {
 #pragma unroll 1
           for (int tap = 0; tap < TAPS; ++tap, ++st) {
             const uint32_t slot = st % NSTAGE;
-            mbar_wait_sleep(B_EMPTY + slot * 8, ((st / NSTAGE) & 1u) ^ 1u);
-            mbar_expect_tx(B_FULL + slot * 8, Cfg::STAGE_BYTES);
-            bulk_g2s(sbase + Cfg::OFF_B + slot * Cfg::STAGE_BYTES, a.w + (size_t)(kc * TAPS + tap) * Cfg::STAGE_BYTES, Cfg::STAGE_BYTES,
-                     B_FULL + slot * 8);
+            mbar_wait_sleep(B_EMPTY + slot * 8, ((st / NSTAGE) & 1u) ^ 1u);      // both CTAs have read the slot's previous stage
+            mbar_expect_tx(B_FULL + slot * 8, Cfg::STAGE_BYTES);                 // own half + the peer's half
+            bulk_g2s_multicast(sbase + Cfg::OFF_B + slot * Cfg::STAGE_BYTES + rank * HALF,
+                               a.w + (size_t)(kc * TAPS + tap) * Cfg::STAGE_BYTES + rank * HALF, HALF, B_FULL + slot * 8, (uint16_t)3);
           }
         }
+      }
+      // the peer's last "slot is free" signals must have landed in THIS CTA's barriers before it exits
+      for (uint32_t k = 0; k < (uint32_t)NSTAGE && k < st; ++k) {
+        const uint32_t s2 = st - 1u - k;
+        mbar_wait_sleep(B_EMPTY + (s2 % NSTAGE) * 8, (s2 / NSTAGE) & 1u);
       }
     }
   } else if (warp == 1) {
@@ -141,9 +171,12 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv(const ConvArgs a) {
     constexpr uint32_t DESC_HI_A = 9u | (1u << 14);                 // A: SBO = 9 rows = 144 B between core matrices, descriptor version 1
     constexpr uint32_t DESC_HI_B = (128u >> 4) | (1u << 14);        // B: SBO = 128 B
     constexpr uint32_t IDESC = make_idesc(N);
-    const uint32_t a_lo_base = ((sbase >> 4) + 16u) | ((uint32_t)QA << 16);   // row 16 of the buffer, LBO = QA rows
+    // descriptor start addresses are CTA-relative 18-bit offsets: in a cluster the shared-window address of rank 1 carries
+    // the CTA rank in its upper bits, which must not spill into the LBO field
+    const uint32_t soff = sbase & 0x3FFFFu;
+    const uint32_t a_lo_base = ((soff >> 4) + 16u) | ((uint32_t)QA << 16);   // row 16 of the buffer, LBO = QA rows
     uint32_t it = 0, st = 0;
-    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+    for (uint32_t pt = pair0; pt < n_pair_tiles; pt += n_pairs_grid, ++it) {
       const uint32_t buf = it & 1u, par = (it >> 1) & 1u;
       mbar_wait(ACC_EMPTY + buf * 8, par ^ 1u);
       tc_fence_after();
@@ -159,14 +192,14 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv(const ConvArgs a) {
           mbar_wait(B_FULL + slot * 8, (st / NSTAGE) & 1u);
           tc_fence_after();
           if (issuer) {
-            const uint32_t b_lo_base = ((sbase + Cfg::OFF_B + slot * Cfg::STAGE_BYTES) >> 4) | ((uint32_t)N << 16);
+            const uint32_t b_lo_base = ((soff + Cfg::OFF_B + slot * Cfg::STAGE_BYTES) >> 4) | ((uint32_t)N << 16);
 #pragma unroll
             for (int kk = 0; kk < 2; ++kk) {
               const uint32_t a_lo = a_lo_base + (uint32_t)(shift + (kc * 4 + kk * 2) * QA);
               const uint32_t b_lo = b_lo_base + (uint32_t)(kk * 2 * N);
               umma_f16(d_tmem, ((uint64_t)DESC_HI_A << 32) | a_lo, ((uint64_t)DESC_HI_B << 32) | b_lo, IDESC, (tap | kc | kk) != 0);
             }
-            umma_commit(B_EMPTY + slot * 8);
+            umma_commit_multicast(B_EMPTY + slot * 8, (uint16_t)3);   // frees the slot in both CTAs
           }
           __syncwarp();
         }
@@ -180,7 +213,8 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv(const ConvArgs a) {
     // ---- epilogue ---------------------------------------------------------------------------------------------
     const int q = warp & 3;                                            // TMEM lane quadrant this warp may read
     uint32_t it = 0;
-    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+    for (uint32_t pt = pair0; pt < n_pair_tiles; pt += n_pairs_grid, ++it) {
+      const uint32_t tile = 2u * pt + rank;
       const uint32_t buf = it & 1u, par = (it >> 1) & 1u;
       mbar_wait(ACC_FULL + buf * 8, par);
       tc_fence_after();
@@ -247,7 +281,9 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_conv(const ConvArgs a) {
     }
   }
   tc_fence_before();
+  __syncwarp();
   __syncthreads();
+  cluster_sync_all();                                                // no CTA leaves while its peer may still signal its barriers
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
@@ -443,7 +479,7 @@ static cudaError_t launch_conv(Net* net, const ConvArgs& a, cudaStream_t stream)
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const uint32_t grid = std::min<uint32_t>((uint32_t)sms, tiles_for(net->max_positions));
+  const uint32_t grid = 2u * std::min<uint32_t>((uint32_t)sms / 2u, (tiles_for(net->max_positions) + 1u) / 2u);   // CTA pairs
   k_conv<KC32, TAPS, N, EPI><<<grid, CONV_THREADS, Cfg::SMEM, stream>>>(a);
   return cudaGetLastError();
 }
