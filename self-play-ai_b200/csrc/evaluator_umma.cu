@@ -85,55 +85,23 @@ static void pack_t(const HostNet& net, std::vector<uint8_t>* out) {
   using Ge = Geo<G>;
   out->assign(image_bytes<G>(), 0);
   uint8_t* img = out->data();
+  // Every conv layer in the kx-triple form: per kernel row ky one block [KC chunks][3N n][8] bf16 whose B rows are the
+  // centre tap (n < N), the right tap (N <= n < 2N) and the left tap (2N <= n < 3N) of that kernel row — one MMA of
+  // width 3N per K step serves all three taps from ONE fetch of A.  3 blocks per layer = the 3 ring groups.
   for (int l = 0; l < N_LAYERS; ++l) {
     const int N = layer_n(l), KC = layer_kchunks(l);
-    if (l >= 1 && l <= 8) {
-      // residual convs: per kernel row ky a 16 KB pair block [8 chunks][128 n][8] (n < 64: centre tap, n >= 64: right
-      // tap) followed by the 8 KB block of the left tap [8 chunks][64 n][8]; 3 x 24 KB = the 9 ring slots of a layer.
-      const HostNet::Conv& cv = net.conv[l];
-      for (int ky = 0; ky < 3; ++ky) {
-        uint16_t* pair = reinterpret_cast<uint16_t*>(img + layer_offset(l) + (size_t)ky * 3 * SLOT_BYTES);
-        uint16_t* left = pair + 2 * SLOT_BYTES / 2;
-        for (int oc = 0; oc < 64; ++oc)
-          for (int k = 0; k < 64; ++k) {
-            const float* w9 = &cv.w[((size_t)oc * cv.ic + k) * 9 + ky * 3];   // [kx = 0 left, 1 centre, 2 right]
-            pair[((size_t)(k / 8) * 128 + oc) * 8 + (k % 8)] = f2bf(w9[1]);
-            pair[((size_t)(k / 8) * 128 + 64 + oc) * 8 + (k % 8)] = f2bf(w9[2]);
-            left[((size_t)(k / 8) * 64 + oc) * 8 + (k % 8)] = f2bf(w9[0]);
-          }
-      }
-      continue;
-    }
-    if (l == 9) {
-      // fused head conv (32 policy + 3 value + 13 zero channels), same kx-pair form: per kernel row a 12 KB pair block
-      // [8 chunks][96 n][8] (n < 48: centre tap, n >= 48: right tap) followed by the 6 KB left-tap block [8 chunks][48 n][8]
-      for (int ky = 0; ky < 3; ++ky) {
-        uint16_t* pair = reinterpret_cast<uint16_t*>(img + layer_offset(l) + (size_t)ky * 3 * layer_tap_bytes(l));
-        uint16_t* left = pair + 8 * 96 * 8;
-        for (int n = 0; n < NET_POLICY_CH + NET_VALUE_CH; ++n) {
-          const HostNet::Conv& cv = n < NET_POLICY_CH ? net.conv[9] : net.conv[10];
-          const int oc = n < NET_POLICY_CH ? n : n - NET_POLICY_CH;
-          for (int k = 0; k < 64; ++k) {
-            const float* w9 = &cv.w[((size_t)oc * cv.ic + k) * 9 + ky * 3];
-            pair[((size_t)(k / 8) * 96 + n) * 8 + (k % 8)] = f2bf(w9[1]);
-            pair[((size_t)(k / 8) * 96 + HEAD_N + n) * 8 + (k % 8)] = f2bf(w9[2]);
-            left[((size_t)(k / 8) * HEAD_N + n) * 8 + (k % 8)] = f2bf(w9[0]);
-          }
-        }
-      }
-      continue;
-    }
-    for (int tap = 0; tap < 9; ++tap) {                          // stem: one block per tap
-      uint16_t* blk = reinterpret_cast<uint16_t*>(img + layer_offset(l) + (size_t)tap * layer_tap_bytes(l));
-      for (int n = 0; n < N; ++n) {
-        const HostNet::Conv* cv;
-        int oc;
-        if (l < 9) { cv = &net.conv[l]; oc = n; }
-        else continue;
-        for (int k = 0; k < KC * 8; ++k) {
-          if (k >= cv->ic) break;
-          float w = cv->w[((size_t)oc * cv->ic + k) * 9 + tap];   // [OC][IC][ky][kx], tap = ky*3+kx
-          blk[((size_t)(k / 8) * N + n) * 8 + (k % 8)] = f2bf(w);
+    const int n_real = l == 9 ? NET_POLICY_CH + NET_VALUE_CH : 64;
+    for (int ky = 0; ky < 3; ++ky) {
+      uint16_t* blk = reinterpret_cast<uint16_t*>(img + layer_offset(l) + (size_t)ky * 3 * layer_tap_bytes(l));
+      for (int n = 0; n < n_real; ++n) {
+        const HostNet::Conv& cv = l < 9 ? net.conv[l] : (n < NET_POLICY_CH ? net.conv[9] : net.conv[10]);
+        const int oc = (l == 9 && n >= NET_POLICY_CH) ? n - NET_POLICY_CH : n;
+        for (int k = 0; k < KC * 8 && k < cv.ic; ++k) {
+          const float* w9 = &cv.w[((size_t)oc * cv.ic + k) * 9 + ky * 3];   // [OC][IC][ky][kx]: kx = 0 left, 1 centre, 2 right
+          uint16_t* row = blk + ((size_t)(k / 8) * 3 * N) * 8 + (k % 8);
+          row[(size_t)n * 8] = f2bf(w9[1]);
+          row[(size_t)(N + n) * 8] = f2bf(w9[2]);
+          row[(size_t)(2 * N + n) * 8] = f2bf(w9[0]);
         }
       }
     }
@@ -163,52 +131,16 @@ void pack_weights(const HostNet& net, std::vector<uint8_t>* out) {
   else pack_t<TicTacToe>(net, out);
 }
 
-// Issues the 9 taps x KSTEPS MMAs of one (layer, tile).  Descriptor low words: A = a_lo_tile + tap shift +
-// kk * 2Q (two K chunks further), B = slot base + tap * slot stride + kk * 2N; high words are constants.
-template <int W8, int Q, int KSTEPS, int N>
-__device__ __forceinline__ void issue_tile(bool issuer, uint32_t a_lo_tile, uint32_t b_lo_base, uint32_t slot_stride16,
-                                           uint32_t d_tmem, bool first_tile, bool last_tile, uint32_t w_par, uint32_t bar_base,
-                                           uint32_t mid_bar, uint32_t mid_par) {
+// Issues the MMAs of one (layer, tile) in the kx-triple form: per kernel row ky, KSTEPS MMAs of width NP = 3N (centre |
+// right | left taps) with A shifted by (ky-1)*W8 rows.  Ring group ky (3 slots = 24 KB) holds the row's block; K step kk
+// reads the K chunks 2kk, 2kk+1 of A (stride Q rows) and of B (stride NP rows).  3 x KSTEPS MMAs per tile-layer (12 for a
+// residual conv instead of 36 one-tap MMAs): A is fetched from shared memory once per kernel row and K step.
+template <int W8, int Q, int KSTEPS, int NP>
+__device__ __forceinline__ void issue_tile_triple(bool issuer, uint32_t a_lo_tile, uint32_t b_lo_base, uint32_t d_tmem,
+                                                  bool first_tile, bool last_tile, uint32_t w_par, uint32_t bar_base,
+                                                  uint32_t mid_bar, uint32_t mid_par) {
   constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);          // SBO = 128 B, descriptor version 1
-  constexpr uint32_t IDESC = make_idesc(N);
-  (void)slot_stride16;
-#pragma unroll
-  for (int tap = 0; tap < 9; ++tap) {
-    if (tap == 6 && mid_bar) {                                    // the bottom kernel row reads the first rows of the next tile
-      mbar_wait(mid_bar, mid_par);
-      tc_fence_after();
-    }
-    if (first_tile && tap % 3 == 0) {                             // w_full[kernel row]: three taps per barrier
-      mbar_wait(bar_base + (uint32_t)(tap / 3) * 8u, w_par);
-      tc_fence_after();
-    }
-    const int shift = (tap / 3 - 1) * W8 + (tap % 3 - 1);
-    if (issuer) {
-#pragma unroll
-      for (int kk = 0; kk < KSTEPS; ++kk) {
-        const uint32_t a_lo = a_lo_tile + (uint32_t)(shift + kk * 2 * Q);
-        const uint32_t b_lo = (b_lo_base + (uint32_t)tap * (SLOT_BYTES >> 4) + (uint32_t)(kk * 2 * N)) | ((uint32_t)N << 16);
-        const uint64_t ad = ((uint64_t)DESC_HI << 32) | a_lo;
-        const uint64_t bd = ((uint64_t)DESC_HI << 32) | b_lo;
-        umma_f16(d_tmem, ad, bd, IDESC, (tap | kk) != 0);
-      }
-      if (last_tile && tap % 3 == 2) umma_commit(bar_base + (uint32_t)(N_SLOTS + tap / 3) * 8u);   // w_empty[kernel row]
-    }
-    __syncwarp();
-  }
-}
-
-// Residual conv, kx-pair form: per kernel row ky 4 MMAs of N=128 (centre | right taps, A shifted by (ky-1)*W8) and
-// 4 MMAs of N=64 (left tap, A shifted one row further back).  Ring slots 3ky, 3ky+1 hold the pair block (K chunks
-// 0..3 / 4..7), slot 3ky+2 the left tap.
-// NP = width of the pair operand (128 residual, 96 head), NL = width of the left tap (64 / 48), LEFT16 = offset of the
-// left-tap block inside the kernel row's ring group in 16-byte units.
-template <int W8, int Q, int NP, int NL, int LEFT16>
-__device__ __forceinline__ void issue_tile_pair(bool issuer, uint32_t a_lo_tile, uint32_t b_lo_base, uint32_t d_tmem,
-                                                bool first_tile, bool last_tile, uint32_t w_par, uint32_t bar_base,
-                                                uint32_t mid_bar, uint32_t mid_par) {
-  constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);
-  constexpr uint32_t IDESC128 = make_idesc(NP), IDESC64 = make_idesc(NL);
+  constexpr uint32_t IDESC = make_idesc(NP);
 #pragma unroll
   for (int ky = 0; ky < 3; ++ky) {
     const int shift = (ky - 1) * W8;
@@ -216,22 +148,16 @@ __device__ __forceinline__ void issue_tile_pair(bool issuer, uint32_t a_lo_tile,
       mbar_wait(mid_bar, mid_par);
       tc_fence_after();
     }
-    if (first_tile) {                                             // w_full[ky]: the three ring slots of this kernel row
+    if (first_tile) {                                             // w_full[ky]: the ring group of this kernel row
       mbar_wait(bar_base + (uint32_t)ky * 8u, w_par);
       tc_fence_after();
     }
     if (issuer) {
 #pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {
+      for (int kk = 0; kk < KSTEPS; ++kk) {
         const uint32_t a_lo = a_lo_tile + (uint32_t)(shift + kk * 2 * Q);
         const uint32_t b_lo = (b_lo_base + (uint32_t)(3 * ky) * (SLOT_BYTES >> 4) + (uint32_t)(kk * 2 * NP)) | ((uint32_t)NP << 16);
-        umma_f16(d_tmem, ((uint64_t)DESC_HI << 32) | a_lo, ((uint64_t)DESC_HI << 32) | b_lo, IDESC128, (ky | kk) != 0);
-      }
-#pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {
-        const uint32_t a_lo = a_lo_tile + (uint32_t)(shift - 1 + kk * 2 * Q);
-        const uint32_t b_lo = (b_lo_base + (uint32_t)(3 * ky) * (SLOT_BYTES >> 4) + (uint32_t)LEFT16 + (uint32_t)(kk * 2 * NL)) | ((uint32_t)NL << 16);
-        umma_f16(d_tmem, ((uint64_t)DESC_HI << 32) | a_lo, ((uint64_t)DESC_HI << 32) | b_lo, IDESC64, 1u);
+        umma_f16(d_tmem, ((uint64_t)DESC_HI << 32) | a_lo, ((uint64_t)DESC_HI << 32) | b_lo, IDESC, (ky | kk) != 0);
       }
       if (last_tile) umma_commit(bar_base + (uint32_t)(N_SLOTS + ky) * 8u);                        // w_empty[ky]
     }
@@ -255,9 +181,9 @@ struct Smem {
   static constexpr int OFF_STATES = OFF_PART + 8 * Ge::NB * 8 * 4;   // part: [8 warps][NB][8 slots] f32; then [2][NB] PState
   static constexpr int OFF_SLOTS = OFF_STATES + 2 * Ge::NB * 16;   // [2][NB] u32 (states/slots ping-pong per batch)
   static constexpr int OFF_BARS = (OFF_SLOTS + 2 * Ge::NB * 4 + 15) & ~15;
-  // barriers: w_full[9], w_empty[9], acc_full[4], act_ready[4], stage_ready[4], acc_full of odd batches [4], act0_free,
-  // head_drained[4], batch[2], claim_go
-  static constexpr int N_BARS = 2 * N_SLOTS + 5 * Ge::NT + 1 + 3 + 2;   // ... + out_ready, out_free
+  // barriers: w_full[9], w_empty[9] (one pair per ring group: 3 used), acc_full[2], acc_drained[2], act_ready[4],
+  // stage_ready[4], act0_free, batch[2], claim_go, out_ready, out_free
+  static constexpr int N_BARS = 2 * N_SLOTS + 4 + 2 * Ge::NT + 1 + 3 + 2;
   static constexpr int OFF_TMEM = OFF_BARS + N_BARS * 8;
   static constexpr int OFF_NB = OFF_TMEM + 16;                     // [4] boards of batch bb (0 = no more batches), [4] = early flag
   static constexpr int TOTAL = OFF_NB + 32;
@@ -300,7 +226,9 @@ __device__ unsigned int g_eval_idx = 0;
 __device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 #define TRACE_ST(b, i) do { if (blockIdx.x == 0 && lane == 0 && (b) >= TRACE_B0 && (b) < TRACE_B0 + 12u) g_trace_stager[(b) - TRACE_B0][i] = clock64(); } while (0)
 #define TRACE2(i) do { if (blockIdx.x == 0 && bb == TRACE_B0 && lane == 0) g_trace[3][480 + (warp == EPI_WARP0 ? 0 : 8) + (i)] = clock64(); } while (0)
+#define TRACE3(i) do { if (blockIdx.x == 0 && bb == TRACE_B0 + 2u && l == 4 && t == 1 && lane == 0 && (warp == EPI_WARP0 || warp == EPI_WARP0 + 4)) g_trace[3][496 + (warp == EPI_WARP0 ? 0 : 8) + (i)] = clock64(); } while (0)
 #else
+#define TRACE3(i) ((void)0)
 #define TRACE2(i) ((void)0)
 #define TRACE(k, b, l, t) ((void)0)
 #define TRACE_ST(b, i) ((void)0)
@@ -329,28 +257,30 @@ k_eval_umma(const uint8_t* __restrict__ image, const EvalWork W, const Trees T, 
   const uint32_t bar_base = s_base + Sm::OFF_BARS;
   auto bar_w_full = [&](int s) { return bar_base + (uint32_t)s * 8u; };
   auto bar_w_empty = [&](int s) { return bar_base + (uint32_t)(N_SLOTS + s) * 8u; };
-  // acc_full is per accumulator set (batch parity): the MMA warp may finish the next batch's stem tile before the
-  // epilogue has consumed this batch's head tile, and an mbarrier must never run two phases ahead of a waiter.
-  auto bar_acc_full = [&](uint32_t set, int t) { return bar_base + (uint32_t)(2 * N_SLOTS + (set ? 3 * Ge::NT : 0) + t) * 8u; };
-  auto bar_act_ready = [&](int t) { return bar_base + (uint32_t)(2 * N_SLOTS + Ge::NT + t) * 8u; };
+  // Accumulators: two sets of 192 TMEM columns (D | E | F = centre | right | left taps; set s at column 256 s).  The tiles
+  // of a CTA form one sequence (batch, layer, tile); tile number g accumulates in set g & 1.  acc_full[s]: the MMAs of the
+  // tile in set s have completed (tcgen05.commit); acc_drained[s]: the epilogue warps have read the set (one arrival per
+  // warp), the tile after next may overwrite it.  The stem of batch b+1 follows the head conv of batch b in the same
+  // sequence, so it runs on the tensor pipe while the epilogue warps are still busy with batch b's head.
+  constexpr uint32_t BAR0 = 2 * N_SLOTS;
+  auto bar_acc_full = [&](uint32_t set) { return bar_base + (BAR0 + set) * 8u; };
+  auto bar_acc_drained = [&](uint32_t set) { return bar_base + (BAR0 + 2u + set) * 8u; };
+  auto bar_act_ready = [&](int t) { return bar_base + (BAR0 + 4u + (uint32_t)t) * 8u; };
   // separate barrier for the staged input of a batch: it may complete while act_ready's previous phase is still
   // being consumed by the MMA warp (an mbarrier must never run two phases ahead of a waiter)
-  auto bar_stage_ready = [&](int t) { return bar_base + (uint32_t)(2 * N_SLOTS + 2 * Ge::NT + t) * 8u; };
+  auto bar_stage_ready = [&](int t) { return bar_base + (BAR0 + 4u + (uint32_t)Ge::NT + (uint32_t)t) * 8u; };
   // activation buffer 0 is free for the next batch's input once every MMA of layer 8 has completed (committed by the MMA warp)
-  const uint32_t bar_act0_free = bar_base + (uint32_t)(2 * N_SLOTS + 4 * Ge::NT) * 8u;
-  // the head conv's accumulators (columns 0..95 of a tile) overlap the next batch's stem accumulators (64..127):
-  // the stem MMAs of tile t wait until the head epilogue has read tile t
-  auto bar_head_drained = [&](int t) { return bar_base + (uint32_t)(2 * N_SLOTS + 4 * Ge::NT + 1 + t) * 8u; };
+  const uint32_t bar_act0_free = bar_base + (BAR0 + 4u + 2u * (uint32_t)Ge::NT) * 8u;
   // batch descriptors: the stager decides how many boards batch bb has (0 = no more batches), writes s_nb[bb & 3] and
   // completes bar_batch[bb & 1]; the producer, the MMA warp and the epilogue warps pick the batch up from there
-  auto bar_batch = [&](uint32_t bb) { return bar_base + (uint32_t)(2 * N_SLOTS + 5 * Ge::NT + 1 + (bb & 1u)) * 8u; };
+  auto bar_batch = [&](uint32_t bb) { return bar_base + (BAR0 + 5u + 2u * (uint32_t)Ge::NT + (bb & 1u)) * 8u; };
   // asynchronous pipeline: the MMA warp arrives when it starts layer 7 of a batch — time for the stager to claim the next
   // batch's leaves from the ring (late enough not to hoard leaves, early enough to have them staged behind the head conv)
-  const uint32_t bar_claim_go = bar_base + (uint32_t)(2 * N_SLOTS + 5 * Ge::NT + 3) * 8u;
+  const uint32_t bar_claim_go = bar_base + (BAR0 + 7u + 2u * (uint32_t)Ge::NT) * 8u;
   // results of a batch (softmax probabilities + value per board, in s_logits) handed from the epilogue warps to the
   // publisher warp, which writes them to global memory and (asynchronous pipeline) pushes the trees to the ready ring
-  const uint32_t bar_out_ready = bar_base + (uint32_t)(2 * N_SLOTS + 5 * Ge::NT + 4) * 8u;
-  const uint32_t bar_out_free = bar_base + (uint32_t)(2 * N_SLOTS + 5 * Ge::NT + 5) * 8u;
+  const uint32_t bar_out_ready = bar_base + (BAR0 + 8u + 2u * (uint32_t)Ge::NT) * 8u;
+  const uint32_t bar_out_free = bar_base + (BAR0 + 9u + 2u * (uint32_t)Ge::NT) * 8u;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + Sm::OFF_TMEM);
   volatile uint32_t* s_nb = reinterpret_cast<volatile uint32_t*>(smem + Sm::OFF_NB);
 
@@ -366,9 +296,9 @@ k_eval_umma(const uint8_t* __restrict__ image, const EvalWork W, const Trees T, 
   }
   if (tid == 0) {
     for (int s = 0; s < N_SLOTS; ++s) { mbar_init(bar_w_full(s), 1); mbar_init(bar_w_empty(s), 1); }
-    for (int t = 0; t < Ge::NT; ++t) { mbar_init(bar_acc_full(0, t), 1); mbar_init(bar_acc_full(1, t), 1); mbar_init(bar_act_ready(t), 256); mbar_init(bar_stage_ready(t), 32); }
+    for (uint32_t set = 0; set < 2; ++set) { mbar_init(bar_acc_full(set), 1); mbar_init(bar_acc_drained(set), N_EPI_WARPS); }
+    for (int t = 0; t < Ge::NT; ++t) { mbar_init(bar_act_ready(t), N_EPI_WARPS); mbar_init(bar_stage_ready(t), 32); }
     mbar_init(bar_act0_free, 1);
-    for (int t = 0; t < Ge::NT; ++t) mbar_init(bar_head_drained(t), 256);
     mbar_init(bar_batch(0), 1); mbar_init(bar_batch(1), 1); mbar_init(bar_claim_go, 1);
     mbar_init(bar_out_ready, 1); mbar_init(bar_out_free, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -410,15 +340,10 @@ k_eval_umma(const uint8_t* __restrict__ image, const EvalWork W, const Trees T, 
         for (int l = 0; l < N_LAYERS; ++l) {
           const uint32_t bytes = (uint32_t)layer_tap_bytes(l);
           const uint8_t* src = image + layer_offset(l);
-          for (int g = 0; g < 3; ++g) {                            // one full/empty barrier pair per kernel row = 3 ring slots
+          for (int g = 0; g < 3; ++g) {                            // one ring group (3 slots) and one full/empty barrier pair per kernel row
             if (use > 0) mbar_wait(bar_w_empty(g), (use - 1) & 1u);
             mbar_expect_tx(bar_w_full(g), 3 * bytes);
-            if (l == 9) {                                          // head: the row's pair + left blocks are one contiguous 18 KB run
-              bulk_g2s(s_base + Sm::OFF_W + (uint32_t)(3 * g) * SLOT_BYTES, src + (size_t)(3 * g) * bytes, 3 * bytes, bar_w_full(g));
-            } else {
-              for (int s = 3 * g; s < 3 * g + 3; ++s)
-                bulk_g2s(s_base + Sm::OFF_W + (uint32_t)s * SLOT_BYTES, src + (size_t)s * bytes, bytes, bar_w_full(g));
-            }
+            bulk_g2s(s_base + Sm::OFF_W + (uint32_t)(3 * g) * SLOT_BYTES, src + (size_t)(3 * g) * bytes, 3 * bytes, bar_w_full(g));
           }
           ++use;
         }
@@ -435,21 +360,18 @@ k_eval_umma(const uint8_t* __restrict__ image, const EvalWork W, const Trees T, 
       uint32_t use = 0;        // layer-uses of the weight ring so far
       uint32_t act_par = 0;    // bit t: parity of the next completion of act_ready[t]
       uint32_t stage_par = 0;  // same for stage_ready[t]
-      uint32_t head_par = 0;   // bit t: parity of the completion of head_drained[t] by the PREVIOUS batch
-      int prev_nt = 0;
+      uint32_t g = 0;          // tiles issued so far: tile g accumulates in TMEM set g & 1
       for (uint32_t b = 0;; ++b) {
         const uint32_t nb = wait_batch(b);
         if (nb == 0u) break;
         const int nt = (int)((nb * Ge::BS + 127) / 128);
-        const uint32_t hp = head_par;                               // parities of the previous batch's head_drained completions
-        head_par ^= (1u << prev_nt) - 1u;
         for (int l = 0; l < N_LAYERS; ++l) {
           if (RING && l == 7 && issuer) mbar_arrive(bar_claim_go);
           const uint32_t in_buf = s_base + ((l == 0 || (l >= 2 && (l & 1) == 0)) ? Sm::OFF_ACT0 : Sm::OFF_ACT1);
           const uint32_t a_lo_base = ((in_buf >> 4) + Ge::LEAD) | ((uint32_t)Ge::Q << 16);
           const uint32_t cur_par = (l == 0) ? stage_par : act_par;
           if (l == 0) stage_par ^= (1u << nt) - 1u; else act_par ^= (1u << nt) - 1u;
-          for (int t = 0; t < nt; ++t) {
+          for (int t = 0; t < nt; ++t, ++g) {
             // A tile's MMAs read its own rows, the last rows of tile t-1 (top kernel row) and the first rows of tile
             // t+1 (bottom kernel row).  Stem: the stager releases tiles in order, wait for tile t+1 up front.  Other
             // layers: wait for tile t (tile 0 only — later tiles were covered by the previous tile's mid-wait) and let
@@ -458,26 +380,25 @@ k_eval_umma(const uint8_t* __restrict__ image, const EvalWork W, const Trees T, 
             if (l == 0) {
               const int wt = min(t + 1, nt - 1);
               mbar_wait(bar_stage_ready(wt), (cur_par >> wt) & 1u);
-              if (t < prev_nt) mbar_wait(bar_head_drained(t), (hp >> t) & 1u);   // the previous batch's head tile t has been read
             } else {
               if (t == 0) mbar_wait(bar_act_ready(0), cur_par & 1u);
               if (t + 1 < nt) { mid_bar = bar_act_ready(t + 1); mid_par = (cur_par >> (t + 1)) & 1u; }
             }
+            const uint32_t set = g & 1u, u = g >> 1;
+            if (u > 0u) mbar_wait(bar_acc_drained(set), (u - 1u) & 1u);   // the tile before last has been read out of this set
             tc_fence_after();
             if (lane == 0) TRACE(0, b, l, t);
             const uint32_t a_lo_tile = a_lo_base + (uint32_t)t * 128u;
-            // 128 columns per tile: D = [0,64) and E = [64,128) (head conv: [0,48) and [48,96)).  The stem accumulates in
-            // columns 64..127; the head_drained wait above keeps it off the previous batch's head columns.
-            const uint32_t d_tmem = tmem_base + (uint32_t)t * 128u + (l == 0 ? 64u : 0u);
+            const uint32_t d_tmem = tmem_base + set * 256u;
             const bool first = (t == 0), last = (t == nt - 1);
             if (l == 0)
-              issue_tile<Ge::W8, Ge::Q, 1, 64>(issuer, a_lo_tile, b_lo_base, 2048 >> 4, d_tmem, first, last, use & 1u, bar_base, 0u, 0u);
+              issue_tile_triple<Ge::W8, Ge::Q, 1, 192>(issuer, a_lo_tile, b_lo_base, d_tmem, first, last, use & 1u, bar_base, 0u, 0u);
             else if (l < 9)
-              issue_tile_pair<Ge::W8, Ge::Q, 128, 64, 1024>(issuer, a_lo_tile, b_lo_base, d_tmem, first, last, use & 1u, bar_base, mid_bar, mid_par);
+              issue_tile_triple<Ge::W8, Ge::Q, 4, 192>(issuer, a_lo_tile, b_lo_base, d_tmem, first, last, use & 1u, bar_base, mid_bar, mid_par);
             else
-              issue_tile_pair<Ge::W8, Ge::Q, 2 * HEAD_N, HEAD_N, 768>(issuer, a_lo_tile, b_lo_base, d_tmem, first, last, use & 1u, bar_base, mid_bar, mid_par);
+              issue_tile_triple<Ge::W8, Ge::Q, 4, 3 * HEAD_N>(issuer, a_lo_tile, b_lo_base, d_tmem, first, last, use & 1u, bar_base, mid_bar, mid_par);
             if (issuer) {
-              umma_commit(bar_acc_full(b & 1u, t));
+              umma_commit(bar_acc_full(set));
               if (l == 8 && last) umma_commit(bar_act0_free);
             }
             __syncwarp();
@@ -485,7 +406,6 @@ k_eval_umma(const uint8_t* __restrict__ image, const EvalWork W, const Trees T, 
           }
           ++use;
         }
-        prev_nt = nt;
       }
     }
   } else if (warp == STAGER_WARP) {
@@ -573,7 +493,7 @@ k_eval_umma(const uint8_t* __restrict__ image, const EvalWork W, const Trees T, 
     uint32_t* s_slots = reinterpret_cast<uint32_t*>(smem + Sm::OFF_SLOTS);
     const float* g_wp = reinterpret_cast<const float*>(image + OFF_WP);
     const float* g_wv = reinterpret_cast<const float*>(image + off_wv<G>());
-    uint32_t acc_par[2] = {0, 0};                                  // [set] bit t: parity of the next completion of acc_full[set][t]
+    uint32_t eg = 0;                                               // tiles read so far: tile eg sits in TMEM set eg & 1 (the MMA warp's sequence)
 
     // Epilogue of conv layer l (0 = stem .. 8) of batch bb: accumulators -> +bias (+skip) -> ReLU -> bf16 -> the other
     // activation buffer, tile by tile; each finished tile releases the next layer's MMAs.
@@ -583,67 +503,75 @@ k_eval_umma(const uint8_t* __restrict__ image, const EvalWork W, const Trees T, 
       const bool in0 = (l == 0 || (l >= 2 && (l & 1) == 0));
       uint8_t* dst_buf = smem + (in0 ? Sm::OFF_ACT1 : Sm::OFF_ACT0);
       const bool has_skip = (l >= 2 && (l & 1) == 0);              // second conv of a residual block
-      const uint32_t cur_par = acc_par[bb & 1u];
-      acc_par[bb & 1u] ^= (1u << nt) - 1u;
+      const bool stash_skip = (l & 1) == 0 && l <= 6;               // the stem and the blocks' second convs produce a block input x
       float bias_r[32];                                             // this thread's 32 output channels, once per layer: a broadcast
 #pragma unroll                                                      // LDS.128 costs two wavefronts of the pipe that bounds this kernel
       for (int q = 0; q < 8; ++q) {
         const float4 bv = *reinterpret_cast<const float4*>(s_bias + l * 64 + half * 32 + q * 4);
         bias_r[4 * q] = bv.x; bias_r[4 * q + 1] = bv.y; bias_r[4 * q + 2] = bv.z; bias_r[4 * q + 3] = bv.w;
       }
-      for (int t = 0; t < nt; ++t) {
+      for (int t = 0; t < nt; ++t, ++eg) {
         const int m = t * 128 + row_in_tile;
         const int bi = m / Ge::BS, rem = m % Ge::BS, r = rem / Ge::W8, c = rem % Ge::W8;
         const bool valid = (uint32_t)bi < nb && r < G::ROWS && c < G::COLS;
         uint8_t* drow = dst_buf + (size_t)(half * 4) * Ge::Q * 16 + (size_t)(Ge::LEAD + m) * 16;   // chunk 4*half
-        uint4 sk[4];
-        if (has_skip) {                                             // (x + f(x)).relu(), model/mod.rs:163
-#pragma unroll
-          for (int j = 0; j < 4; ++j) sk[j] = *reinterpret_cast<const uint4*>(drow + (size_t)j * Ge::Q * 16);
-        }
-        mbar_wait(bar_acc_full(bb & 1u, t), (cur_par >> t) & 1u);
+        const uint32_t set = eg & 1u;
+        TRACE3(0);
+        mbar_wait(bar_acc_full(set), (eg >> 1) & 1u);
         tc_fence_after();
         if (et == 0) TRACE(2, bb, l, t);
-        // stem: E half, no shift.  Residual convs: out[r] = D[r] + E[r+1] (the right tap was computed one row early);
-        // lane 31 is a pad cell (row 32k-1), so the shuffle never has to cross a warp.
-        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)t * 128u + (uint32_t)half * 32u;
-        uint32_t a[32];
-        if (l == 0) {
-          tmem_ld16(taddr + 64u, a);
-          tmem_ld16(taddr + 80u, a + 16);
-          tmem_ld_wait();
-        } else {
-          uint32_t e[32];
-          tmem_ld16(taddr, a);
-          tmem_ld16(taddr + 16u, a + 16);
-          tmem_ld16(taddr + 64u, e);
-          tmem_ld16(taddr + 80u, e + 16);
-          tmem_ld_wait();
-#pragma unroll
-          for (int q = 0; q < 32; ++q)
-            a[q] = __float_as_uint(__uint_as_float(a[q]) + __uint_as_float(__shfl_down_sync(0xffffffffu, e[q], 1)));
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {                               // one 8-channel chunk = one 16-B store
-          float v[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(a[j * 8 + e]) + bias_r[j * 8 + e];
-          if (has_skip) {
-            v[0] += bf_lo(sk[j].x); v[1] += bf_hi(sk[j].x); v[2] += bf_lo(sk[j].y); v[3] += bf_hi(sk[j].y);
-            v[4] += bf_lo(sk[j].z); v[5] += bf_hi(sk[j].z); v[6] += bf_lo(sk[j].w); v[7] += bf_hi(sk[j].w);
-          }
-          uint4 o = make_uint4(0, 0, 0, 0);
-          if (valid) {
-            o.x = pack_bf16x2(fmaxf(v[0], 0.f), fmaxf(v[1], 0.f));
-            o.y = pack_bf16x2(fmaxf(v[2], 0.f), fmaxf(v[3], 0.f));
-            o.z = pack_bf16x2(fmaxf(v[4], 0.f), fmaxf(v[5], 0.f));
-            o.w = pack_bf16x2(fmaxf(v[6], 0.f), fmaxf(v[7], 0.f));
-          }
-          *reinterpret_cast<uint4*>(drow + (size_t)j * Ge::Q * 16) = o;
-        }
-        fence_async_smem();
+        TRACE3(1);
+        // out[r] = D[r] + E[r+1] + F[r-1]: the right tap was computed one row early, the left tap one row late.  Rows
+        // 32k-1 are pad cells: lane 31 never needs E of the next warp (its output is a pad cell) and lane 0 takes F = 0
+        // (F of a pad-column row is a sum over pad-column cells, which are zero).
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + set * 256u + (uint32_t)half * 32u;
+        uint32_t a[32], e[32], f[32];
+        tmem_ld16(taddr, a);
+        tmem_ld16(taddr + 16u, a + 16);
+        tmem_ld16(taddr + 64u, e);
+        tmem_ld16(taddr + 80u, e + 16);
+        tmem_ld16(taddr + 128u, f);
+        tmem_ld16(taddr + 144u, f + 16);
+        tmem_ld_wait();
         tc_fence_before();
-        mbar_arrive(bar_act_ready(t));
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_acc_drained(set));           // the tile after next may accumulate in this set
+        TRACE3(2);
+#pragma unroll
+        for (int q = 0; q < 32; ++q) {
+          const float ev = __uint_as_float(__shfl_down_sync(0xffffffffu, e[q], 1));
+          const float fv = __uint_as_float(__shfl_up_sync(0xffffffffu, f[q], 1));
+          float v = __uint_as_float(a[q]) + ev;
+          if (lane != 0) v += fv;
+          a[q] = __float_as_uint(v);
+        }
+        TRACE3(3);
+        // The skip connection (x + f(x)).relu(), model/mod.rs:163, comes from TMEM: the epilogue that produced x (the stem
+        // or the previous block's second conv) left this thread's 32 channels, as stored (bf16 pairs), in the 16 spare
+        // columns of an accumulator set — no shared-memory read on the pipe the tensor core needs.
+        const uint32_t skaddr = tmem_base + ((uint32_t)(quad * 32) << 16) + ((t & 1) ? 448u : 192u) + (uint32_t)(t >> 1) * 32u + (uint32_t)half * 16u;
+        uint32_t sk[16];
+        if (has_skip) tmem_ld16(skaddr, sk);
+        float v[32];
+#pragma unroll
+        for (int q = 0; q < 32; ++q) v[q] = __uint_as_float(a[q]) + bias_r[q];
+        if (has_skip) {
+          tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 16; ++q) { v[2 * q] += bf_lo(sk[q]); v[2 * q + 1] += bf_hi(sk[q]); }
+        }
+        uint32_t o[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) o[q] = valid ? pack_relu_bf16x2(v[2 * q], v[2 * q + 1]) : 0u;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)                                 // one 8-channel chunk = one 16-B store
+          *reinterpret_cast<uint4*>(drow + (size_t)j * Ge::Q * 16) = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+        if (stash_skip) { tmem_st16(skaddr, o); tmem_st_wait(); }   // this layer's output is the next block's x
+        TRACE3(4);
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_act_ready(t));
+        TRACE3(5);
         if (et == 0) TRACE(3, bb, l, t);
       }
     };
@@ -654,32 +582,39 @@ k_eval_umma(const uint8_t* __restrict__ image, const EvalWork W, const Trees T, 
     auto head_epilogue = [&](uint32_t bb) {
       const uint32_t nb = s_nb[bb & 3u];
       const int nt = (int)((nb * Ge::BS + 127) / 128);
-      const uint32_t cur_par = acc_par[bb & 1u];
-      acc_par[bb & 1u] ^= (1u << nt) - 1u;
       const float* bias = s_bias + 9 * 64;
-      for (int t = 0; t < nt; ++t) {
+      for (int t = 0; t < nt; ++t, ++eg) {
         const int m = t * 128 + row_in_tile;
         const int bi = m / Ge::BS, rem = m % Ge::BS, r = rem / Ge::W8, c = rem % Ge::W8;
         const bool valid = (uint32_t)bi < nb && r < G::ROWS && c < G::COLS;
-        mbar_wait(bar_acc_full(bb & 1u, t), (cur_par >> t) & 1u);
+        const uint32_t set = eg & 1u;
+        mbar_wait(bar_acc_full(set), (eg >> 1) & 1u);
         tc_fence_after();
         if (et == 0) TRACE(2, bb, 9, t);
-        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)t * 128u;
-        // columns [0,48) = D (centre + left taps), [48,96) = E (right tap, one row early): out[r] = D[r] + E[r+1]
-        uint32_t a[16], av[16], e[16], ev[16];
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + set * 256u;
+        // columns [0,48) = D (centre taps), [48,96) = E (right taps, one row early), [96,144) = F (left taps, one row late)
+        uint32_t a[16], av[4], e[16], ev[4], f[16], fv[4];
         tmem_ld16(taddr + (uint32_t)half * 16u, a);
         tmem_ld16(taddr + (uint32_t)HEAD_N + (uint32_t)half * 16u, e);
-        if (half == 1) { tmem_ld16(taddr + 32u, av); tmem_ld16(taddr + (uint32_t)HEAD_N + 32u, ev); }
+        tmem_ld16(taddr + 2u * (uint32_t)HEAD_N + (uint32_t)half * 16u, f);
+        if (half == 1) { tmem_ld4(taddr + 32u, av); tmem_ld4(taddr + (uint32_t)HEAD_N + 32u, ev); tmem_ld4(taddr + 2u * (uint32_t)HEAD_N + 32u, fv); }
         tmem_ld_wait();
         tc_fence_before();
-        mbar_arrive(bar_head_drained(t));                           // the next batch's stem may overwrite columns 64..127 of this tile
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_acc_drained(set));
 #pragma unroll
-        for (int q = 0; q < 16; ++q)
-          a[q] = __float_as_uint(__uint_as_float(a[q]) + __uint_as_float(__shfl_down_sync(0xffffffffu, e[q], 1)));
+        for (int q = 0; q < 16; ++q) {
+          const float e1 = __uint_as_float(__shfl_down_sync(0xffffffffu, e[q], 1));
+          const float f1 = __uint_as_float(__shfl_up_sync(0xffffffffu, f[q], 1));
+          a[q] = __float_as_uint((__uint_as_float(a[q]) + e1) + (lane == 0 ? 0.0f : f1));
+        }
         if (half == 1) {                                            // warp-uniform: half is a property of the warp
 #pragma unroll
-          for (int q = 0; q < 3; ++q)
-            av[q] = __float_as_uint(__uint_as_float(av[q]) + __uint_as_float(__shfl_down_sync(0xffffffffu, ev[q], 1)));
+          for (int q = 0; q < 3; ++q) {
+            const float e1 = __uint_as_float(__shfl_down_sync(0xffffffffu, ev[q], 1));
+            const float f1 = __uint_as_float(__shfl_up_sync(0xffffffffu, fv[q], 1));
+            av[q] = __float_as_uint((__uint_as_float(av[q]) + e1) + (lane == 0 ? 0.0f : f1));
+          }
         }
         if (valid) {
           uint8_t* prow = smem + Sm::OFF_ACT0 + (size_t)(Ge::LEAD + m) * 16;
@@ -847,22 +782,23 @@ k_eval_umma(const uint8_t* __restrict__ image, const EvalWork W, const Trees T, 
     if (nb_cur != 0u) conv_epilogue(0, 0);
     for (uint32_t b = 0; nb_cur != 0u; ++b) {
       for (int l = 1; l < 9; ++l) conv_epilogue(b, l);
-      float w_heads[8][8];
-      load_head_weights(w_heads, 0);                                // in flight during the head conv's epilogue
       head_epilogue(b);
       // Has the stager already decided the next batch?  One thread looks, so that all 256 epilogue threads take the
       // same branch (both branches contain named barriers).
       if (et == 0) s_nb[4] = mbar_test(bar_batch(b + 1), ((b + 1) >> 1) & 1u) ? s_nb[(b + 1) & 3u] : NOT_YET;
       epi_bar_sync();                                               // every head activation of the batch is in shared memory
       uint32_t nb_next = s_nb[4];
+      float w_heads[8][8];                                          // loaded after the stem epilogue: 64 more live registers there would spill
       if (nb_next != NOT_YET) {
         // The stem of the next batch ran on the tensor pipe behind this batch's head conv (the stager had its input
         // ready): release layer 1 of the next batch before spending time on this batch's Linear layers.
         if (nb_next != 0u) conv_epilogue(b + 1, 0);
+        load_head_weights(w_heads, 0);
         linear_heads(b, w_heads);
       } else {
         // The next batch is not known yet (few leaves in flight): its leaves may depend on THIS batch's results, so the
         // results go out first.
+        load_head_weights(w_heads, 0);
         linear_heads(b, w_heads);
         nb_next = wait_batch(b + 1);
         if (nb_next != 0u) conv_epilogue(b + 1, 0);

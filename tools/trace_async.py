@@ -55,3 +55,8 @@ with S.Engine(game=S.GAME_C4, num_games=G, evaluator=S.EVAL_NET, max_nodes_per_t
     s = tr[3][480:486]
     print("linear_heads(first traced batch) warp 2: start %d | weights +%d | board loop +%d | cross-warp sum +%d | softmax +%d | sync +%d" % (
         s[0] - t0, s[1] - s[0], s[2] - s[1], s[3] - s[2], s[4] - s[3], s[5] - s[4]))
+    for w, name in ((0, "first epilogue warp (half 0)"), (8, "fifth epilogue warp (half 1)")):
+        s = tr[3][496 + w:496 + w + 6]
+        if s[0]:
+            print("conv epilogue of (batch +2, layer 4, tile 1), %s: wait acc_full +%d | tcgen05.ld x6 + wait + drained +%d | 64 shuffles + adds +%d | skip, bias, ReLU, 4 stores +%d | fence + arrive +%d" % (
+                name, s[1] - s[0], s[2] - s[1], s[3] - s[2], s[4] - s[3], s[5] - s[4]))
