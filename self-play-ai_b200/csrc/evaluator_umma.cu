@@ -537,13 +537,14 @@ k_eval_umma(const uint8_t* __restrict__ image, const EvalWork W, const Trees T, 
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_acc_drained(set));           // the tile after next may accumulate in this set
         TRACE3(2);
+        float v[32];
 #pragma unroll
-        for (int q = 0; q < 32; ++q) {
-          const float ev = __uint_as_float(__shfl_down_sync(0xffffffffu, e[q], 1));
-          const float fv = __uint_as_float(__shfl_up_sync(0xffffffffu, f[q], 1));
-          float v = __uint_as_float(a[q]) + ev;
-          if (lane != 0) v += fv;
-          a[q] = __float_as_uint(v);
+        for (int q = 0; q < 32; q += 2) {                           // packed f32x2 adds: two channels per instruction
+          const float e0 = __uint_as_float(__shfl_down_sync(0xffffffffu, e[q], 1)), e1 = __uint_as_float(__shfl_down_sync(0xffffffffu, e[q + 1], 1));
+          const float f0 = __uint_as_float(__shfl_up_sync(0xffffffffu, f[q], 1)), f1 = __uint_as_float(__shfl_up_sync(0xffffffffu, f[q + 1], 1));
+          v[q] = __uint_as_float(a[q]); v[q + 1] = __uint_as_float(a[q + 1]);
+          add2(v[q], v[q + 1], e0, e1);
+          if (lane != 0) add2(v[q], v[q + 1], f0, f1);
         }
         TRACE3(3);
         // The skip connection (x + f(x)).relu(), model/mod.rs:163, comes from TMEM: the epilogue that produced x (the stem
@@ -552,13 +553,12 @@ k_eval_umma(const uint8_t* __restrict__ image, const EvalWork W, const Trees T, 
         const uint32_t skaddr = tmem_base + ((uint32_t)(quad * 32) << 16) + ((t & 1) ? 448u : 192u) + (uint32_t)(t >> 1) * 32u + (uint32_t)half * 16u;
         uint32_t sk[16];
         if (has_skip) tmem_ld16(skaddr, sk);
-        float v[32];
 #pragma unroll
-        for (int q = 0; q < 32; ++q) v[q] = __uint_as_float(a[q]) + bias_r[q];
+        for (int q = 0; q < 32; q += 2) add2(v[q], v[q + 1], bias_r[q], bias_r[q + 1]);
         if (has_skip) {
           tmem_ld_wait();
 #pragma unroll
-          for (int q = 0; q < 16; ++q) { v[2 * q] += bf_lo(sk[q]); v[2 * q + 1] += bf_hi(sk[q]); }
+          for (int q = 0; q < 16; ++q) add2(v[2 * q], v[2 * q + 1], bf_lo(sk[q]), bf_hi(sk[q]));
         }
         uint32_t o[16];
 #pragma unroll
@@ -606,7 +606,9 @@ k_eval_umma(const uint8_t* __restrict__ image, const EvalWork W, const Trees T, 
         for (int q = 0; q < 16; ++q) {
           const float e1 = __uint_as_float(__shfl_down_sync(0xffffffffu, e[q], 1));
           const float f1 = __uint_as_float(__shfl_up_sync(0xffffffffu, f[q], 1));
-          a[q] = __float_as_uint((__uint_as_float(a[q]) + e1) + (lane == 0 ? 0.0f : f1));
+          float v = __uint_as_float(a[q]) + e1;
+          if (lane != 0) v += f1;
+          a[q] = __float_as_uint(v);
         }
         if (half == 1) {                                            // warp-uniform: half is a property of the warp
 #pragma unroll
@@ -668,24 +670,14 @@ k_eval_umma(const uint8_t* __restrict__ image, const EvalWork W, const Trees T, 
         }
       }
     };
-    // w_first: the weights of the first output group, loaded by the caller before the head conv's epilogue so that their
-    // latency is off the critical path (the Linear layers sit between the stem and layer 1 of the next batch).
-    auto linear_heads = [&](uint32_t bb, float (&w_first)[8][8]) {
+    // Board loop of the Linear layers for the output group og (weights w): every warp leaves its partial sums in s_part.
+    auto heads_partials = [&](uint32_t bb, float (&w)[8][8]) {
       const uint32_t nb = s_nb[bb & 3u];
       float* s_part = reinterpret_cast<float*>(smem + Sm::OFF_PART);   // [8 warps][NB][8 slots]
       const int we = warp - EPI_WARP0;
       const uint32_t roff = (uint32_t)((is_pol || is_val ? (2 + c4) * Ge::Q * 16 : 0) + ((pos / G::COLS) * Ge::W8 + (pos % G::COLS)) * 16);
       TRACE2(0);
-      for (int og = 0; og < NOUT; og += 8) {
-        float w[8][8];
-        if (og == 0) {
-#pragma unroll
-          for (int s = 0; s < 8; ++s)
-#pragma unroll
-            for (int j = 0; j < 8; ++j) w[s][j] = w_first[s][j];
-        } else {
-          load_head_weights(w, og);
-        }
+      {
         TRACE2(1);
         const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
         // three boards per trip so that the loads, FMA chains and shuffle levels of different boards overlap
@@ -736,52 +728,77 @@ k_eval_umma(const uint8_t* __restrict__ image, const EvalWork W, const Trees T, 
           }
         }
         TRACE2(2);
-        epi_bar_sync();
-        if (og == 0 && bb > 0) mbar_wait(bar_out_free, (bb - 1) & 1u);   // the publisher has read the previous batch's results
-        for (int i = et; i < (int)nb * 8; i += 256) {
-          const int bi = i >> 3, s = i & 7, o = og + s;
-          if (o < NOUT) {
-            float acc = 0.0f;
-#pragma unroll
-            for (int wv_ = 0; wv_ < 8; ++wv_) acc += s_part[((size_t)wv_ * Ge::NB + bi) * 8 + s];
-            s_logits[bi * 16 + (o == G::A ? 15 : o)] = acc;
-          }
-        }
-        epi_bar_sync();
       }
+    };
+    // The 8 warp partials of every (board, slot) are added in warp order: the summation order of a board is fixed.
+    auto heads_reduce = [&](uint32_t bb, int og) {
+      const uint32_t nb = s_nb[bb & 3u];
+      const float* s_part = reinterpret_cast<const float*>(smem + Sm::OFF_PART);
+      epi_bar_sync();
+      if (og == 0 && bb > 0) mbar_wait(bar_out_free, (bb - 1) & 1u);   // the publisher has read the previous batch's results
+      for (int i = et; i < (int)nb * 8; i += 256) {
+        const int bi = i >> 3, sl = i & 7, o = og + sl;
+        if (o < NOUT) {
+          float acc = 0.0f;
+#pragma unroll
+          for (int wv_ = 0; wv_ < 8; ++wv_) acc += s_part[((size_t)wv_ * Ge::NB + bi) * 8 + sl];
+          s_logits[bi * 16 + (o == G::A ? 15 : o)] = acc;
+        }
+      }
+      epi_bar_sync();
       TRACE2(3);
-      if ((uint32_t)et < nb) {                                      // one thread per board
-        const float* fcb = s_bias + N_LAYERS * 64;
-        float lg[G::A];
-        float mx = -INFINITY;
+    };
+    // softmax (model/mod.rs:63) and tanh (connect_four.rs:71): LG lanes per board, lane a < A owns action a, the last lane
+    // of the group the value.  The normaliser is the sum of the exponentials in action order (one lane would produce the
+    // same bits).  The board's record (softmax probabilities, value) replaces its logits in s_logits: the publisher warp
+    // writes it to global memory, so that the global stores and the release of the trees are not on the epilogue warps' path.
+    auto heads_softmax = [&](uint32_t bb) {
+      const uint32_t nb = s_nb[bb & 3u];
+      constexpr int LG = G::A <= 7 ? 8 : 16;
+      const float* fcb = s_bias + N_LAYERS * 64;
+      const int a = et % LG;
+      for (uint32_t bi = (uint32_t)(et / LG); bi < ((nb + 256 / LG - 1) / (256 / LG)) * (256 / LG); bi += 256 / LG) {   // warp-uniform trip count
+        const bool live = bi < nb;
+        const float raw = live ? s_logits[bi * 16 + (a == LG - 1 ? 15 : a)] : 0.0f;
+        const float lg = (a < G::A) ? raw + fcb[a] : -INFINITY;
+        float mx = lg;
 #pragma unroll
-        for (int a = 0; a < G::A; ++a) { lg[a] = s_logits[et * 16 + a] + fcb[a]; mx = fmaxf(mx, lg[a]); }
-        float ex[G::A], sum = 0.0f;
+        for (int o = LG / 2; o >= 1; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        const float ex = (a < G::A) ? expf(lg - mx) : 0.0f;
+        float sum = 0.0f;
 #pragma unroll
-        for (int a = 0; a < G::A; ++a) { ex[a] = expf(lg[a] - mx); sum += ex[a]; }
-        const float val = tanhf(s_logits[et * 16 + 15] + fcb[16]);
-        // the board's record (softmax probabilities, value) replaces its logits in s_logits: the publisher warp writes it to
-        // global memory, so that the global stores and the release of the trees are not on the epilogue warps' path
-#pragma unroll
-        for (int a = 0; a < G::A; ++a) s_logits[et * 16 + a] = ex[a] / sum;
-        s_logits[et * 16 + 15] = val;
-        if (logits_out) {                                           // spb_predict(raw_logits) only
-          const uint32_t slot = s_slots[(bb & 1u) * Ge::NB + et];
-#pragma unroll
-          for (int a = 0; a < G::A; ++a) logits_out[(size_t)slot * G::A + a] = lg[a];
+        for (int k = 0; k < G::A; ++k) sum += __shfl_sync(0xffffffffu, ex, (lane & ~(LG - 1)) + k);
+        if (live) {
+          if (a < G::A) s_logits[bi * 16 + a] = ex / sum;
+          else if (a == LG - 1) s_logits[bi * 16 + 15] = tanhf(raw + fcb[16]);
+          if (logits_out && a < G::A) logits_out[(size_t)s_slots[(bb & 1u) * Ge::NB + bi] * G::A + a] = lg;   // spb_predict(raw_logits) only
         }
       }
       TRACE2(4);
-      epi_bar_sync();                                               // the records are complete; buffer 0 is free for layer 1
+      epi_bar_sync();                                               // the records are complete
       if (et == 0) mbar_arrive(bar_out_ready);
       TRACE2(5);
+    };
+    // The two Linear layers, softmax and tanh of batch bb.  w_first: the weights of the first output group.
+    auto linear_heads = [&](uint32_t bb, float (&w_first)[8][8]) {
+      heads_partials(bb, w_first);
+      heads_reduce(bb, 0);
+      for (int og = 8; og < NOUT; og += 8) {
+        float w[8][8];
+        load_head_weights(w, og);
+        heads_partials(bb, w);
+        heads_reduce(bb, og);
+      }
+      heads_softmax(bb);
     };
 
     constexpr uint32_t NOT_YET = 0xFFFFFFFFu;
     uint32_t nb_cur = wait_batch(0);
     if (nb_cur != 0u) conv_epilogue(0, 0);
+    bool l1_done = false;                                           // layer 1 of this batch was handled inside the previous batch's heads
     for (uint32_t b = 0; nb_cur != 0u; ++b) {
-      for (int l = 1; l < 9; ++l) conv_epilogue(b, l);
+      for (int l = l1_done ? 2 : 1; l < 9; ++l) conv_epilogue(b, l);
+      l1_done = false;
       head_epilogue(b);
       // Has the stager already decided the next batch?  One thread looks, so that all 256 epilogue threads take the
       // same branch (both branches contain named barriers).
@@ -794,7 +811,18 @@ k_eval_umma(const uint8_t* __restrict__ image, const EvalWork W, const Trees T, 
         // ready): release layer 1 of the next batch before spending time on this batch's Linear layers.
         if (nb_next != 0u) conv_epilogue(b + 1, 0);
         load_head_weights(w_heads, 0);
-        linear_heads(b, w_heads);
+        if (NOUT <= 8 && nb_next != 0u) {
+          // Only the board loop reads the head activations in buffer 0, which layer 1's epilogue overwrites: the reduction,
+          // softmax and hand-off to the publisher follow layer 1 of the next batch, whose MMAs would otherwise wait for them
+          // (two accumulator sets: the MMA warp is at most two tiles ahead of the epilogue warps).
+          heads_partials(b, w_heads);
+          conv_epilogue(b + 1, 1);
+          l1_done = true;
+          heads_reduce(b, 0);
+          heads_softmax(b);
+        } else {
+          linear_heads(b, w_heads);
+        }
       } else {
         // The next batch is not known yet (few leaves in flight): its leaves may depend on THIS batch's results, so the
         // results go out first.
