@@ -497,9 +497,9 @@ k_eval_umma(const uint8_t* __restrict__ image, const EvalWork W, const Trees T, 
 
     // Epilogue of conv layer l (0 = stem .. 8) of batch bb: accumulators -> +bias (+skip) -> ReLU -> bf16 -> the other
     // activation buffer, tile by tile; each finished tile releases the next layer's MMAs.
-    auto conv_epilogue = [&](uint32_t bb, int l) {
+    auto conv_epilogue = [&](uint32_t bb, int l, int t_begin = 0, int t_end = Ge::NT) {
       const uint32_t nb = s_nb[bb & 3u];
-      const int nt = (int)((nb * Ge::BS + 127) / 128);
+      const int nt = min((int)((nb * Ge::BS + 127) / 128), t_end);
       const bool in0 = (l == 0 || (l >= 2 && (l & 1) == 0));
       uint8_t* dst_buf = smem + (in0 ? Sm::OFF_ACT1 : Sm::OFF_ACT0);
       const bool has_skip = (l >= 2 && (l & 1) == 0);              // second conv of a residual block
@@ -510,7 +510,7 @@ k_eval_umma(const uint8_t* __restrict__ image, const EvalWork W, const Trees T, 
         const float4 bv = *reinterpret_cast<const float4*>(s_bias + l * 64 + half * 32 + q * 4);
         bias_r[4 * q] = bv.x; bias_r[4 * q + 1] = bv.y; bias_r[4 * q + 2] = bv.z; bias_r[4 * q + 3] = bv.w;
       }
-      for (int t = 0; t < nt; ++t, ++eg) {
+      for (int t = t_begin; t < nt; ++t, ++eg) {
         const int m = t * 128 + row_in_tile;
         const int bi = m / Ge::BS, rem = m % Ge::BS, r = rem / Ge::W8, c = rem % Ge::W8;
         const bool valid = (uint32_t)bi < nb && r < G::ROWS && c < G::COLS;
@@ -671,8 +671,9 @@ k_eval_umma(const uint8_t* __restrict__ image, const EvalWork W, const Trees T, 
       }
     };
     // Board loop of the Linear layers for the output group og (weights w): every warp leaves its partial sums in s_part.
-    auto heads_partials = [&](uint32_t bb, float (&w)[8][8]) {
+    auto heads_partials = [&](uint32_t bb, float (&w)[8][8], uint32_t bi_begin = 0, uint32_t bi_end = Ge::NB) {   // bi_begin: a multiple of 3
       const uint32_t nb = s_nb[bb & 3u];
+      const uint32_t bend = min(nb, bi_end);
       float* s_part = reinterpret_cast<float*>(smem + Sm::OFF_PART);   // [8 warps][NB][8 slots]
       const int we = warp - EPI_WARP0;
       const uint32_t roff = (uint32_t)((is_pol || is_val ? (2 + c4) * Ge::Q * 16 : 0) + ((pos / G::COLS) * Ge::W8 + (pos % G::COLS)) * 16);
@@ -684,8 +685,8 @@ k_eval_umma(const uint8_t* __restrict__ image, const EvalWork W, const Trees T, 
         uint4 vn[3];                                                // the next trip's activations, fetched a trip ahead
 #pragma unroll
         for (int k = 0; k < 3; ++k)
-          vn[k] = *reinterpret_cast<const uint4*>(smem + Sm::OFF_ACT0 + (size_t)(Ge::LEAD + min((uint32_t)k, nb - 1u) * Ge::BS) * 16 + roff);
-        for (uint32_t bi0 = 0; bi0 < nb; bi0 += 3) {
+          vn[k] = *reinterpret_cast<const uint4*>(smem + Sm::OFF_ACT0 + (size_t)(Ge::LEAD + min(bi_begin + (uint32_t)k, nb - 1u) * Ge::BS) * 16 + roff);
+        for (uint32_t bi0 = bi_begin; bi0 < bend; bi0 += 3) {
           float sres[3];
           uint4 v[3];
 #pragma unroll
@@ -814,8 +815,11 @@ k_eval_umma(const uint8_t* __restrict__ image, const EvalWork W, const Trees T, 
         if (NOUT <= 8 && nb_next != 0u) {
           // Only the board loop reads the head activations in buffer 0, which layer 1's epilogue overwrites: the reduction,
           // softmax and hand-off to the publisher follow layer 1 of the next batch, whose MMAs would otherwise wait for them
-          // (two accumulator sets: the MMA warp is at most two tiles ahead of the epilogue warps).
+          // (two accumulator sets: the MMA warp is at most two tiles ahead of the epilogue warps).  Interleaving the board
+          // loop with layer 1's tiles was tried: the 64 weight registers do not survive the conv epilogue (spills inside
+          // the board loop, 81 ms instead of 65 ms per search).
           heads_partials(b, w_heads);
+          epi_bar_sync();                                           // every warp has read the head activations: buffer 0 may be overwritten
           conv_epilogue(b + 1, 1);
           l1_done = true;
           heads_reduce(b, 0);
