@@ -3,13 +3,14 @@
 // Replaces Net::forward (ref: src/model/mod.rs:152-184, src/model/connect_four.rs:50-81, src/model/tictactoe.rs:50-81)
 // and the tensor part of Model::predict (src/model/mod.rs:60-67,95).  One persistent CTA per SM runs the whole network
 // on batches of <= NB boards with the activations resident in shared memory:
-//   warp 0      weight producer: cp.async.bulk of the BN-folded bf16 weights into a 9-slot ring (mbarrier complete_tx)
-//   warp 1      MMA issuer: tcgen05.mma.cta_group::1.kind::f16, M = 128, accumulators in TMEM (512 columns)
-//   warps 2-9   epilogue: tcgen05.ld -> +bias (+skip) -> ReLU -> bf16 -> the other activation buffer; Linear heads,
-//               softmax, tanh
-//   warp 10     stager: fetches the leaf positions of the next batch and writes their encoding (get_encoding,
+//   warp 0      weight producer: cp.async.bulk of the BN-folded bf16 weights into a 3-group ring (mbarrier complete_tx)
+//   warp 1      MMA issuer: tcgen05.mma.cta_group::1.kind::f16, M = 128, accumulators in TMEM (two sets of 192 columns)
+//   warp 2      stager: fetches the leaf positions of the next batch and writes their encoding (get_encoding,
 //               connect_four.rs:242-259) as the stem's input
-//   warps 11+   (asynchronous search pipeline only) tree warps: expand + backup + select of mcts.rs, see async.cuh
+//   warp 3      publisher: results to global memory, evaluated trees to the ready ring
+//   warps 4-11  epilogue: tcgen05.ld -> +bias (+skip) -> ReLU -> bf16 -> the other activation buffer; Linear heads,
+//               softmax, tanh
+//   warps 12-15 (asynchronous search pipeline only) tree warps: expand + backup + select of mcts.rs, see async.cuh
 // Work comes either from a static list (spb_predict, lock-step pipeline: RING = false) or from the leaf ring of the
 // asynchronous search pipeline (RING = true), where the kernel stays resident for a whole spb_search.
 //
@@ -17,14 +18,15 @@
 // row shared with the next board), so tap (dy,dx) is the constant row offset dy*8+dx of the UMMA descriptor's start
 // address.  Measured on B200 (tools/umma_probe.cu T5): one thread issues one tcgen05.mma per ~46 cycles and an
 // M=128,N=64,K=16 MMA needs 48 cycles of operand fetch, so one MMA per tap is bound by ISSUE + shared-memory fetch of A
-// (4 KB per MMA re-read for every tap), not by the tensor pipe (32 cycles).  Therefore the centre and right taps of a kernel row (kx = 0, +1) share ONE A fetch: their weights sit side by side as
-// a N=128 B operand, so one MMA (64 cycles, tensor-bound) yields D (columns 0..63, centre tap, final position) and E
-// (columns 64..127, right tap, computed one row early).  The left tap (kx = -1) stays a N=64 MMA with A shifted by
-// one row, accumulating into D.  24 MMAs per tile-layer instead of 36; the epilogue forms out[r] = D[r] + E[r+1]
-// with one warp shuffle per channel — row r+1 of lane 31 is never needed because rows 32k-1 are pad cells.
-// The fused head conv has the same form (N = 96 + 48).  Accumulators: 128 TMEM columns per tile, 4 tiles = 512 columns; the
-// stem of the next batch accumulates in columns 64..127 of a tile once the head epilogue has read that tile (head_drained),
-// which keeps the overlap of batch b+1's stem with batch b's head.
+// (4 KB per MMA, re-read for every tap), not by the tensor pipe (32 cycles).  Therefore the three taps of a kernel row
+// (kx = 0, +1, -1) share ONE A fetch: their weights sit side by side as an N = 192 B operand, so one MMA (96 cycles,
+// tensor-bound) yields D (columns 0..63, centre tap, final position), E (columns 64..127, right tap, computed one row
+// early) and F (columns 128..191, left tap, one row late).  12 MMAs per tile-layer instead of 36; the epilogue forms
+// out[r] = D[r] + E[r+1] + F[r-1] with two warp shuffles per channel — rows 32k-1 are pad cells, so lane 31 never needs
+// E of the next warp and lane 0 takes F = 0 (F of a pad-column row is a sum over pad-column cells, which are zero).
+// The stem (one K step) and the fused head conv (N = 3 x 48) have the same form.  Accumulators: two sets of 192 TMEM
+// columns used in rotation by the CTA's tile sequence (batch, layer, tile); the spare 2 x 64 columns carry the skip
+// connection of the residual blocks from the epilogue that produced it to the epilogue that adds it.
 #include <cuda_bf16.h>
 
 #include <cstring>
