@@ -14,6 +14,7 @@ namespace chess {
 
 constexpr int WARPS = 4;
 constexpr int THREADS = WARPS * 32;
+constexpr uint32_t SPLIT_MIN_TREES = 128;   // the network pipeline runs as two half-loops on two streams from 2 x this many trees on
 
 __global__ void k_chess_reset(CTrees T, const uint32_t* slots, const Pos* roots, const unsigned long long* hist, uint32_t n) {
   const uint32_t i = blockIdx.x;
@@ -128,12 +129,12 @@ __global__ void __launch_bounds__(THREADS) k_chess_search_fused(CTrees T, uint32
 // ---- lock-step pipeline for the network --------------------------------------------------------------------------
 // k_chess_select: the select of one simulation per tree; terminal leaves are backed up at once, the others are stored
 // with their legal moves as the tree's pending leaf and appended to the evaluator's work list (mcts.rs:236-252).
-__global__ void __launch_bounds__(THREADS) k_chess_select(CTrees T) {
+__global__ void __launch_bounds__(THREADS) k_chess_select(CTrees T, TreeRange R) {
   __shared__ WarpScratch s_ws[WARPS];
   const int lane = threadIdx.x & 31;
   WarpScratch& ws = s_ws[threadIdx.x >> 5];
-  const uint32_t g = blockIdx.x * WARPS + (threadIdx.x >> 5);
-  if (g >= T.G || !T.live[g]) return;
+  const uint32_t g = R.g0 + blockIdx.x * WARPS + (threadIdx.x >> 5);
+  if (g >= R.g1 || !T.live[g]) return;
   const uint32_t b = T.buf[g];
   uint4* rec = T.rec[b] + (size_t)g * T.cap;
   uint2* meta = T.meta[b] + (size_t)g * T.cap;
@@ -171,7 +172,7 @@ __global__ void __launch_bounds__(THREADS) k_chess_select(CTrees T) {
       T.leaf_nmoves[g] = (uint32_t)n;
       T.leaf_reps[g] = reps;
       T.leaf_hash[g] = h;
-      T.eval_list[atomicAdd(T.eval_count, 1u)] = g;
+      R.list[atomicAdd(R.count, 1u)] = g;
     }
   }
   flush_counters(T, ctr, lane);
@@ -184,13 +185,16 @@ __global__ void __launch_bounds__(THREADS) k_chess_select(CTrees T) {
 // RAW = true (parity harness, SPB_FLAG_FORCE_SPLIT): eval_logits holds the raw probabilities of a built-in evaluator for the
 // legal cells (k_chess_builtin_eval) and the prior is raw / sum, exactly as in the fused kernel.
 template <bool RAW>
-__global__ void __launch_bounds__(THREADS) k_chess_finish(CTrees T) {
+__global__ void __launch_bounds__(THREADS) k_chess_finish(CTrees T, TreeRange R) {
   __shared__ WarpScratch s_ws[WARPS];
-  __shared__ float s_e[WARPS][MAX_MOVES];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   WarpScratch& ws = s_ws[w];
-  const uint32_t g = blockIdx.x * WARPS + w;
-  if (g >= T.G || !T.live[g]) return;
+  // the exponentials of the legal logits live in the scratch's path-hash array, which this kernel does not use: 10 KB of
+  // shared memory per block, so that a block fits next to a resident k_conv CTA (chess_net.cu)
+  static_assert(sizeof(ws.phash) >= MAX_MOVES * sizeof(float), "phash too small for the priors");
+  float* s_ev = reinterpret_cast<float*>(ws.phash);
+  const uint32_t g = R.g0 + blockIdx.x * WARPS + w;
+  if (g >= R.g1 || !T.live[g]) return;
   const uint32_t ld = T.leaf_depth[g];
   if (!(ld & LEAF_PENDING)) return;
   const int depth = (int)(ld & 0xFFu);
@@ -208,22 +212,22 @@ __global__ void __launch_bounds__(THREADS) k_chess_finish(CTrees T) {
   float mx = -INFINITY;
   for (int i = lane; i < n; i += 32) {
     const float l = logits[policy_index(side, ws.moves[i])];
-    s_e[w][i] = l;
+    s_ev[i] = l;
     mx = fmaxf(mx, l);
   }
 #pragma unroll
   for (int o = 16; o >= 1; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   float sum = 0.0f;
   for (int i = lane; i < n; i += 32) {
-    const float e = RAW ? s_e[w][i] : __expf(s_e[w][i] - mx);
-    s_e[w][i] = e;
+    const float e = RAW ? s_ev[i] : __expf(s_ev[i] - mx);
+    s_ev[i] = e;
     sum += e;                                                        // RAW: dyadic values, exact in any order
   }
 #pragma unroll
   for (int o = 16; o >= 1; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
   __syncwarp();
   uint32_t n_nodes = T.n_nodes[g];
-  const float* ev = s_e[w];
+  const float* ev = s_ev;
   const bool ok = expand(rec, meta, hash, T.cap, n_nodes, node, ws, n, T.leaf_hash[g], lane, [&](int i) { return __fdiv_rn(ev[i], sum); });
   if (!ok) {
     if (lane == 0) { atomicOr(T.error, (uint32_t)ERRBIT_POOL); T.leaf_depth[g] = 0; }
@@ -241,11 +245,11 @@ __global__ void __launch_bounds__(THREADS) k_chess_finish(CTrees T) {
 // Built-in evaluators for the lock-step pipeline (parity harness): the raw probabilities of the legal cells and the value of
 // every pending leaf, where the network would have written its logits.
 template <int EVAL>
-__global__ void __launch_bounds__(THREADS) k_chess_builtin_eval(CTrees T) {
+__global__ void __launch_bounds__(THREADS) k_chess_builtin_eval(CTrees T, TreeRange R) {
   const int lane = threadIdx.x & 31;
   const uint32_t i = blockIdx.x * WARPS + (threadIdx.x >> 5);
-  if (i >= *T.eval_count) return;
-  const uint32_t g = T.eval_list[i];
+  if (i >= *R.count) return;
+  const uint32_t g = R.list[i];
   const Pos pos = T.leaf_pos[g];
   const uint64_t dh = det_hash(pos);
   const int n = (int)T.leaf_nmoves[g];
@@ -433,7 +437,9 @@ int32_t spb_chess_create(const spb_config* cfg, spb_chess_engine** out) {
   cudaDeviceProp prop;
   if (cudaSetDevice(cfg->device) != cudaSuccess || cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess) return fail(SPB_ERR_CUDA, "cudaSetDevice failed");
   if (prop.major != 10) return fail(SPB_ERR_CUDA, "device is not sm_100 (B200); this library is built for sm_100a only");
-  if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&e->ev0) != cudaSuccess ||
+  if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&e->stream2, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreate(&e->ev0) != cudaSuccess ||
       cudaEventCreate(&e->ev1) != cudaSuccess)
     return fail(SPB_ERR_CUDA, "stream / event creation failed");
   ch::CTrees& T = e->T;
@@ -461,7 +467,7 @@ int32_t spb_chess_create(const spb_config* cfg, spb_chess_engine** out) {
   if (!rc) rc = e->dalloc(&T.leaf_reps, G);
   if (!rc) rc = e->dalloc(&T.leaf_hash, G);
   if (!rc) rc = e->dalloc(&T.eval_list, G);
-  if (!rc) rc = e->dalloc(&T.eval_count, 1);
+  if (!rc) rc = e->dalloc(&T.eval_count, 2);
   if (!rc) rc = e->dalloc(&T.eval_value, G);
   if (!rc && (cfg->evaluator == SPB_EVAL_NET || (cfg->flags & SPB_FLAG_FORCE_SPLIT))) rc = e->dalloc(&T.eval_logits, G * (size_t)ch::LOGIT_STRIDE);
   if (!rc) rc = e->dalloc(&e->d_rc_moves, G * ch::MAX_MOVES);
@@ -476,7 +482,7 @@ int32_t spb_chess_create(const spb_config* cfg, spb_chess_engine** out) {
   cudaMemsetAsync(T.leaf_depth, 0, G * 4, e->stream);
   cudaMemsetAsync(T.counters, 0, CTR_COUNT * 8, e->stream);
   cudaMemsetAsync(T.error, 0, 4, e->stream);
-  cudaMemsetAsync(T.eval_count, 0, 4, e->stream);
+  cudaMemsetAsync(T.eval_count, 0, 8, e->stream);
   if (cudaStreamSynchronize(e->stream) != cudaSuccess) return fail(SPB_ERR_CUDA, "device initialisation failed");
   *out = e;
   return SPB_OK;
@@ -490,6 +496,9 @@ int32_t spb_chess_destroy(spb_chess_engine* e) {
   for (void* p : e->allocs) cudaFree(p);
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
+  if (e->stream2) cudaStreamDestroy(e->stream2);
+  if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+  if (e->ev_join) cudaEventDestroy(e->ev_join);
   if (e->stream) cudaStreamDestroy(e->stream);
   delete e;
   return SPB_OK;
@@ -530,27 +539,49 @@ int32_t spb_chess_search(spb_chess_engine* e, uint32_t num_searches) {
   if (num_searches == 0) return SPB_OK;
   const uint32_t blocks = (e->T.G + ch::WARPS - 1) / ch::WARPS;
   CH_CUDA(e, cudaEventRecord(e->ev0, e->stream));
+  const ch::TreeRange all{0u, e->T.G, e->T.eval_list, e->T.eval_count};
   if (e->cfg.evaluator == SPB_EVAL_NET) {
     CH_ARG(e, e->net && ch::net_loaded(e->net), "no weights loaded (spb_chess_load_weights)");
-    for (uint32_t s = 0; s < num_searches; ++s) {                      // mcts.rs:214: one evaluator batch per simulation step
-      CH_CUDA(e, cudaMemsetAsync(e->T.eval_count, 0, 4, e->stream));
-      ch::k_chess_select<<<blocks, ch::THREADS, 0, e->stream>>>(e->T);
-      CH_CUDA(e, cudaGetLastError());
-      uint32_t launched = 0;
-      const int32_t rc = ch::net_forward_leaves(e, &launched);
-      if (rc) return rc;
-      ch::k_chess_finish<false><<<blocks, ch::THREADS, 0, e->stream>>>(e->T);
-      CH_CUDA(e, cudaGetLastError());
-      e->launches += 2 + launched;
+    // mcts.rs:214: one evaluator batch per simulation step.  Trees never interact, so the lock-step loop runs separately
+    // over the two halves of the trees, on two streams: while the convolutions of one half hold the tensor pipes, the
+    // select / expand + backup kernels of the other half run in the SMs' spare issue slots and shared memory (a k_conv CTA
+    // leaves room for them).  Results are those of one loop over all trees (tests: node for node against the oracle).
+    const uint32_t G = e->T.G, G0 = (G + 1u) / 2u;
+    const bool split = G >= 2u * ch::SPLIT_MIN_TREES && !(e->cfg.flags & SPB_FLAG_LOCKSTEP);
+    const ch::TreeRange half[2] = {{0u, split ? G0 : G, e->T.eval_list, e->T.eval_count}, {G0, G, e->T.eval_list + G0, e->T.eval_count + 1}};
+    const int nh = split ? 2 : 1;
+    cudaStream_t st[2] = {e->stream, e->stream2};
+    if (split) {
+      CH_CUDA(e, cudaEventRecord(e->ev_fork, e->stream));
+      CH_CUDA(e, cudaStreamWaitEvent(e->stream2, e->ev_fork, 0));
+    }
+    for (uint32_t s = 0; s < num_searches; ++s) {
+      for (int h = 0; h < nh; ++h) {
+        const ch::TreeRange& R = half[h];
+        const uint32_t hb = (R.g1 - R.g0 + ch::WARPS - 1) / ch::WARPS;
+        CH_CUDA(e, cudaMemsetAsync(R.count, 0, 4, st[h]));
+        ch::k_chess_select<<<hb, ch::THREADS, 0, st[h]>>>(e->T, R);
+        CH_CUDA(e, cudaGetLastError());
+        uint32_t launched = 0;
+        const int32_t rc = ch::net_forward_leaves(e, h, R.list, R.count, st[h], &launched);
+        if (rc) return rc;
+        ch::k_chess_finish<false><<<hb, ch::THREADS, 0, st[h]>>>(e->T, R);
+        CH_CUDA(e, cudaGetLastError());
+        e->launches += 2 + launched;
+      }
+    }
+    if (split) {
+      CH_CUDA(e, cudaEventRecord(e->ev_join, e->stream2));
+      CH_CUDA(e, cudaStreamWaitEvent(e->stream, e->ev_join, 0));
     }
   } else if (e->cfg.flags & SPB_FLAG_FORCE_SPLIT) {
     // parity harness: the built-in evaluators through the kernels of the network pipeline (select -> evaluate -> finish)
     for (uint32_t s = 0; s < num_searches; ++s) {
       CH_CUDA(e, cudaMemsetAsync(e->T.eval_count, 0, 4, e->stream));
-      ch::k_chess_select<<<blocks, ch::THREADS, 0, e->stream>>>(e->T);
-      if (e->cfg.evaluator == SPB_EVAL_DET) ch::k_chess_builtin_eval<SPB_EVAL_DET><<<blocks, ch::THREADS, 0, e->stream>>>(e->T);
-      else ch::k_chess_builtin_eval<SPB_EVAL_UNIFORM><<<blocks, ch::THREADS, 0, e->stream>>>(e->T);
-      ch::k_chess_finish<true><<<blocks, ch::THREADS, 0, e->stream>>>(e->T);
+      ch::k_chess_select<<<blocks, ch::THREADS, 0, e->stream>>>(e->T, all);
+      if (e->cfg.evaluator == SPB_EVAL_DET) ch::k_chess_builtin_eval<SPB_EVAL_DET><<<blocks, ch::THREADS, 0, e->stream>>>(e->T, all);
+      else ch::k_chess_builtin_eval<SPB_EVAL_UNIFORM><<<blocks, ch::THREADS, 0, e->stream>>>(e->T, all);
+      ch::k_chess_finish<true><<<blocks, ch::THREADS, 0, e->stream>>>(e->T, all);
       CH_CUDA(e, cudaGetLastError());
       e->launches += 3;
     }

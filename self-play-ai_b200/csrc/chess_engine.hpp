@@ -22,8 +22,8 @@ struct spb_chess_engine {
   spb_config cfg{};
   std::string err;
   spb::chess::CTrees T{};
-  cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaStream_t stream = nullptr, stream2 = nullptr;   // stream2: the second half of the trees in the network pipeline
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_join = nullptr;
   std::vector<void*> allocs;
   spb::chess::Net* net = nullptr;
   uint64_t launches = 0;

@@ -51,7 +51,10 @@ constexpr int LEAD = 16;              // zero rows in front of the first positio
 constexpr int TILE_BROWS = 16;                    // board rows per tile
 constexpr int TILE_SPAN = TILE_BROWS * 9;         // layout rows one tile spans: 144
 constexpr int QA = 16 + (TILE_BROWS - 1) * 9 + 8 + 10;   // rows of an A tile in shared memory: 16 halo + 143 + 10 halo = 169
-constexpr int NSTAGE = 8;             // weight ring depth
+#ifndef SPB_CHESS_NSTAGE
+#define SPB_CHESS_NSTAGE 8
+#endif
+constexpr int NSTAGE = SPB_CHESS_NSTAGE;   // weight ring depth
 constexpr int CONV_THREADS = 192;
 constexpr int IN_CHUNKS = 4;          // stem input: 19 planes padded to 32 channels
 
@@ -84,9 +87,13 @@ struct ConvArgs {
   uint32_t plane_rows;
   float* logits;            // EPI 2: [slot][4672]
   const uint32_t* list;     // EPI 2: slot of position i (nullptr: identity)
+  const float* vw;          // EPI 3: the value head's 1x1 conv weights [256] (model/chess.rs:61)
+  float* vcell;             // EPI 3: [position of the batch][64] f32: that conv's output before bias and ReLU
 };
 
-enum { EPI_RELU = 0, EPI_SKIP_RELU = 1, EPI_LOGITS = 2 };
+// EPI_SKIP_RELU_VALUE: the torso's last conv; its epilogue also forms the value head's 1x1 conv (256 -> 1) of the cell it
+// holds in registers, so the value head never reads the torso output back from HBM
+enum { EPI_RELU = 0, EPI_SKIP_RELU = 1, EPI_LOGITS = 2, EPI_SKIP_RELU_VALUE = 3 };
 
 template <int KC32, int TAPS, int N, int EPI>
 struct ConvCfg {
@@ -96,7 +103,8 @@ struct ConvCfg {
   static constexpr uint32_t GROUP_BYTES = 4u * QA * 16;       // one 32-channel group of the A tile
   static constexpr uint32_t OFF_B = A_BYTES;
   static constexpr uint32_t OFF_BIAS = OFF_B + NSTAGE * STAGE_BYTES;
-  static constexpr uint32_t OFF_BAR = OFF_BIAS + 256 * 4;
+  static constexpr uint32_t OFF_VW = OFF_BIAS + 256 * 4;
+  static constexpr uint32_t OFF_BAR = OFF_VW + (EPI == 3 ? 256 * 4 : 0);
   static constexpr uint32_t SMEM = OFF_BAR + 48 * 8;
 };
 
@@ -112,6 +120,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) k_c
                  B_EMPTY = bar0 + 160 + NSTAGE * 8;
   uint32_t* tmem_word = reinterpret_cast<uint32_t*>(smem + Cfg::OFF_BAR + 46 * 8);
   float* s_bias = reinterpret_cast<float*>(smem + Cfg::OFF_BIAS);
+  float* s_vw = reinterpret_cast<float*>(smem + Cfg::OFF_VW);
 
   const uint32_t boards = *a.count;
   const uint32_t n_tiles = tiles_for(boards);
@@ -126,6 +135,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) k_c
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int i = threadIdx.x; i < N; i += CONV_THREADS) s_bias[i] = a.bias[i];
+  if (EPI == EPI_SKIP_RELU_VALUE)
+    for (int i = threadIdx.x; i < N; i += CONV_THREADS) s_vw[i] = a.vw[i];
   if (warp == 1) tmem_alloc(smem_u32(tmem_word), 512);
   tc_fence_before();
   __syncthreads();
@@ -242,13 +253,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) k_c
         }
       } else {
         uint8_t* orow = a.out + ((size_t)LEAD + r_layout) * 16;
+        float vdot = 0.0f;
 #pragma unroll 1
         for (int c32 = 0; c32 < N / 32; ++c32) {
           uint32_t r[32];
           tmem_ld16(taddr + c32 * 32, r);
           tmem_ld16(taddr + c32 * 32 + 16, r + 16);
           uint4 sk[4];
-          if (EPI == EPI_SKIP_RELU && !pad) {
+          if ((EPI == EPI_SKIP_RELU || EPI == EPI_SKIP_RELU_VALUE) && !pad) {
 #pragma unroll
             for (int c = 0; c < 4; ++c) sk[c] = *reinterpret_cast<const uint4*>(orow + (size_t)(c32 * 4 + c) * a.plane_rows * 16);
           }
@@ -260,10 +272,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) k_c
               float v[8];
 #pragma unroll
               for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[c * 8 + j]) + s_bias[ch0 + j];
-              if (EPI == EPI_SKIP_RELU) {
+              if (EPI == EPI_SKIP_RELU || EPI == EPI_SKIP_RELU_VALUE) {
                 const uint32_t s4[4] = {sk[c].x, sk[c].y, sk[c].z, sk[c].w};
 #pragma unroll
                 for (int j = 0; j < 4; ++j) { v[2 * j] += bf_lo(s4[j]); v[2 * j + 1] += bf_hi(s4[j]); }
+              }
+              if (EPI == EPI_SKIP_RELU_VALUE) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) vdot = fmaf(fmaxf(v[j], 0.f), s_vw[ch0 + j], vdot);
               }
               uint4 o;
               o.x = pack_bf16x2(fmaxf(v[0], 0.f), fmaxf(v[1], 0.f));
@@ -274,6 +290,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) k_c
             }
           }
         }
+        if (EPI == EPI_SKIP_RELU_VALUE && !pad) a.vcell[(size_t)board * 64 + y * 8 + x] = vdot;
       }
       tc_fence_before();
       __syncwarp();
@@ -315,50 +332,62 @@ __global__ void k_encode_input(const Pos* pos, const uint32_t* reps, const uint3
   }
 }
 
-// ---- value head (model/chess.rs:61-70): 1x1 conv 256 -> 1, ReLU, Linear 64 -> 256, ReLU, Linear 256 -> 1, tanh ----------
-// One block of 256 threads per position; f32 weights, bf16 torso output.
-__global__ void __launch_bounds__(256) k_value_head(const uint8_t* x, uint32_t plane_rows, const uint32_t* list, const uint32_t* count,
-                                                    const float* vconv_w, const float* vconv_b, const float* fc1_w, const float* fc1_b,
-                                                    const float* fc2_w, const float* fc2_b, float* values) {
-  __shared__ float s_part[4][64];
-  __shared__ float s_cell[64];
-  __shared__ float s_red[8];
-  const uint32_t board = blockIdx.x;
-  if (board >= *count) return;
-  const int t = threadIdx.x, cell = t & 63, part = t >> 6;             // 4 threads per cell, 8 chunks each
-  const uint32_t r = board * BOARD_ROWS + (cell / 8) * 9 + (cell % 8);
-  float acc = 0.0f;
-  for (int c = part * 8; c < part * 8 + 8; ++c) {
-    const uint4 u = *reinterpret_cast<const uint4*>(x + ((size_t)c * plane_rows + LEAD + r) * 16);
-    const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc += bf_lo(w4[j]) * vconv_w[c * 8 + 2 * j] + bf_hi(w4[j]) * vconv_w[c * 8 + 2 * j + 1];
+// ---- value head (model/chess.rs:61-70): 1x1 conv 256 -> 1 (formed in the last torso conv's epilogue: vcell), + bias, ReLU,
+// Linear 64 -> 256, ReLU, Linear 256 -> 1, tanh.  One block of 256 threads per VH_POS positions: thread t owns hidden unit t
+// and reads its 64 fc1 weights once for all of them.
+constexpr int VH_POS = 8;
+__global__ void __launch_bounds__(256) k_value_head(const float* vcell, const uint32_t* list, const uint32_t* count, const float* vconv_b,
+                                                    const float* fc1_w, const float* fc1_b, const float* fc2_w, const float* fc2_b, float* values) {
+  __shared__ float s_cell[VH_POS][64];
+  __shared__ float s_red[VH_POS][8];
+  const uint32_t n = *count, b0 = blockIdx.x * VH_POS;
+  if (b0 >= n) return;
+  const int t = threadIdx.x;
+  const float vb = vconv_b[0];
+  for (int i = t; i < VH_POS * 64; i += 256) {
+    const uint32_t board = b0 + (uint32_t)(i >> 6);
+    s_cell[i >> 6][i & 63] = board < n ? fmaxf(vcell[(size_t)board * 64 + (i & 63)] + vb, 0.0f) : 0.0f;
   }
-  s_part[part][cell] = acc;
   __syncthreads();
-  if (t < 64) s_cell[t] = fmaxf(s_part[0][t] + s_part[1][t] + s_part[2][t] + s_part[3][t] + vconv_b[0], 0.0f);
-  __syncthreads();
-  float h = fc1_b[t];
-  for (int k = 0; k < 64; ++k) h += fc1_w[k * 256 + t] * s_cell[k];   // fc1_w is stored transposed [64][256]: coalesced over t
-  float y = fmaxf(h, 0.0f) * fc2_w[t];
+  float h[VH_POS];
+  const float hb = fc1_b[t];
 #pragma unroll
-  for (int o = 16; o >= 1; o >>= 1) y += __shfl_xor_sync(0xffffffffu, y, o);
-  if ((t & 31) == 0) s_red[t >> 5] = y;
+  for (int p = 0; p < VH_POS; ++p) h[p] = hb;
+  for (int k = 0; k < 64; ++k) {
+    const float w = fc1_w[k * 256 + t];                              // fc1_w is stored transposed [64][256]: coalesced over t
+#pragma unroll
+    for (int p = 0; p < VH_POS; ++p) h[p] += w * s_cell[p][k];
+  }
+  const float w2 = fc2_w[t];
+#pragma unroll
+  for (int p = 0; p < VH_POS; ++p) {
+    float y = fmaxf(h[p], 0.0f) * w2;
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) y += __shfl_xor_sync(0xffffffffu, y, o);
+    if ((t & 31) == 0) s_red[p][t >> 5] = y;
+  }
   __syncthreads();
-  if (t == 0) {
-    float s = fc2_b[0];
-    for (int i = 0; i < 8; ++i) s += s_red[i];
-    values[list ? list[board] : board] = tanhf(s);
+  if (t < VH_POS && b0 + (uint32_t)t < n) {
+    float sum = fc2_b[0];
+    for (int i = 0; i < 8; ++i) sum += s_red[t][i];
+    const uint32_t board = b0 + (uint32_t)t;
+    values[list ? list[board] : board] = tanhf(sum);
   }
 }
 
 // ---- host ------------------------------------------------------------------------------------------------------------
-struct Net {
+// Activation buffers of one evaluator batch.  Set 0 holds up to the engine's num_games positions (spb_chess_predict, the
+// first half of the trees in the search), set 1 the second half of the trees (chess_engine.cu: two half-loops on two streams).
+struct ActSet {
   uint32_t max_positions = 0;
   size_t plane_rows = 0;
   uint8_t* d_in = nullptr;      // [4][plane_rows][8] bf16
   uint8_t* d_x = nullptr;       // [32][plane_rows][8]
   uint8_t* d_y = nullptr;
+  float* d_vcell = nullptr;     // [max_positions][64] f32: the value head's 1x1 conv, from the last torso conv's epilogue
+};
+struct Net {
+  ActSet act[2];
   uint8_t* d_w = nullptr;       // weight image
   size_t w_bytes = 0;
   size_t off_conv[NET_CONV3] = {}, off_p1 = 0, off_p2 = 0;
@@ -394,9 +423,8 @@ static void pack_conv(const HostNet::Conv& cv, int kc32, int N, uint16_t* dst) {
 Net* net_create(uint32_t max_positions, std::string* err) {
   Net* net = new (std::nothrow) Net();
   if (!net) { *err = "out of host memory"; return nullptr; }
-  net->max_positions = max_positions;
-  net->plane_rows = plane_rows_for(max_positions);
-  const size_t plane = net->plane_rows * 16;
+  net->act[0].max_positions = max_positions;
+  net->act[1].max_positions = std::max(1u, max_positions / 2u);
   size_t w = 0;
   for (int i = 0; i < NET_CONV3; ++i) { net->off_conv[i] = w; w += (size_t)9 * (i == 0 ? 1 : 8) * 4 * 256 * 16; }
   net->off_p1 = w; w += (size_t)8 * 4 * 256 * 16;
@@ -412,23 +440,31 @@ Net* net_create(uint32_t max_positions, std::string* err) {
   net->off_f1b = f; f += 256;
   net->off_f2w = f; f += 256;
   net->off_f2b = f; f += 8;
-  if (cudaMalloc(&net->d_in, IN_CHUNKS * plane) != cudaSuccess || cudaMalloc(&net->d_x, 32 * plane) != cudaSuccess ||
-      cudaMalloc(&net->d_y, 32 * plane) != cudaSuccess || cudaMalloc(&net->d_w, net->w_bytes) != cudaSuccess ||
-      cudaMalloc(&net->d_f, f * 4) != cudaSuccess) {
+  bool ok = cudaMalloc(&net->d_w, net->w_bytes) == cudaSuccess && cudaMalloc(&net->d_f, f * 4) == cudaSuccess;
+  for (int k = 0; k < 2 && ok; ++k) {
+    ActSet& a = net->act[k];
+    a.plane_rows = plane_rows_for(a.max_positions);
+    const size_t plane = a.plane_rows * 16;
+    ok = cudaMalloc(&a.d_in, IN_CHUNKS * plane) == cudaSuccess && cudaMalloc(&a.d_x, 32 * plane) == cudaSuccess &&
+         cudaMalloc(&a.d_y, 32 * plane) == cudaSuccess && cudaMalloc(&a.d_vcell, (size_t)a.max_positions * 64 * 4) == cudaSuccess;
+    if (ok) {                                                         // lead / tail rows are never written by a kernel: zero once
+      cudaMemset(a.d_in, 0, IN_CHUNKS * plane);
+      cudaMemset(a.d_x, 0, 32 * plane);
+      cudaMemset(a.d_y, 0, 32 * plane);
+    }
+  }
+  if (!ok) {
     *err = "out of device memory for the chess network's activations";
     net_destroy(net);
     return nullptr;
   }
-  // lead / tail rows are never written by a kernel: zero once
-  cudaMemset(net->d_in, 0, IN_CHUNKS * plane);
-  cudaMemset(net->d_x, 0, 32 * plane);
-  cudaMemset(net->d_y, 0, 32 * plane);
   return net;
 }
 
 void net_destroy(Net* net) {
   if (!net) return;
-  cudaFree(net->d_in); cudaFree(net->d_x); cudaFree(net->d_y); cudaFree(net->d_w); cudaFree(net->d_f);
+  for (ActSet& a : net->act) { cudaFree(a.d_in); cudaFree(a.d_x); cudaFree(a.d_y); cudaFree(a.d_vcell); }
+  cudaFree(net->d_w); cudaFree(net->d_f);
   delete net;
 }
 
@@ -468,7 +504,7 @@ bool net_upload(Net* net, const HostNet& h, std::string* err) {
 }
 
 template <int KC32, int TAPS, int N, int EPI>
-static cudaError_t launch_conv(Net* net, const ConvArgs& a, cudaStream_t stream) {
+static cudaError_t launch_conv(const ActSet& act, const ConvArgs& a, cudaStream_t stream) {
   using Cfg = ConvCfg<KC32, TAPS, N, EPI>;
   static bool attr = false;
   if (!attr) {
@@ -479,42 +515,45 @@ static cudaError_t launch_conv(Net* net, const ConvArgs& a, cudaStream_t stream)
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const uint32_t grid = 2u * std::min<uint32_t>((uint32_t)sms / 2u, (tiles_for(net->max_positions) + 1u) / 2u);   // CTA pairs
+  const uint32_t grid = 2u * std::min<uint32_t>((uint32_t)sms / 2u, (tiles_for(act.max_positions) + 1u) / 2u);   // CTA pairs
   k_conv<KC32, TAPS, N, EPI><<<grid, CONV_THREADS, Cfg::SMEM, stream>>>(a);
   return cudaGetLastError();
 }
 
-cudaError_t net_forward(Net* net, const Pos* pos, const uint32_t* reps, const uint32_t* list, const uint32_t* count_dev, float* logits,
+cudaError_t net_forward(Net* net, int set, const Pos* pos, const uint32_t* reps, const uint32_t* list, const uint32_t* count_dev, float* logits,
                         float* values, cudaStream_t stream, uint32_t* launched) {
-  const uint32_t plane_rows = (uint32_t)net->plane_rows;
-  const uint32_t max_rows = tiles_for(net->max_positions) * TILE_SPAN;
+  const ActSet& act = net->act[set];
+  const uint32_t plane_rows = (uint32_t)act.plane_rows;
+  const uint32_t max_rows = tiles_for(act.max_positions) * TILE_SPAN;
   uint32_t n = 0;
   cudaError_t e;
-  k_encode_input<<<(max_rows + 127) / 128, 128, 0, stream>>>(pos, reps, list, count_dev, net->d_in, plane_rows);
+  k_encode_input<<<(max_rows + 127) / 128, 128, 0, stream>>>(pos, reps, list, count_dev, act.d_in, plane_rows);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   ++n;
   ConvArgs a{};
   a.count = count_dev; a.plane_rows = plane_rows; a.list = list; a.logits = logits;
   // stem: x = relu(bn(conv(in)))
-  a.in = net->d_in; a.out = net->d_x; a.w = net->d_w + net->off_conv[0]; a.bias = net->d_f + net->off_bias[0];
-  if ((e = launch_conv<1, 9, 256, EPI_RELU>(net, a, stream)) != cudaSuccess) return e;
+  a.in = act.d_in; a.out = act.d_x; a.w = net->d_w + net->off_conv[0]; a.bias = net->d_f + net->off_bias[0];
+  if ((e = launch_conv<1, 9, 256, EPI_RELU>(act, a, stream)) != cudaSuccess) return e;
   ++n;
   for (int b = 0; b < NET_BLOCKS; ++b) {                               // resnet_block, model/mod.rs:152-166
-    a.in = net->d_x; a.out = net->d_y; a.w = net->d_w + net->off_conv[1 + 2 * b]; a.bias = net->d_f + net->off_bias[1 + 2 * b];
-    if ((e = launch_conv<8, 9, 256, EPI_RELU>(net, a, stream)) != cudaSuccess) return e;
-    a.in = net->d_y; a.out = net->d_x; a.w = net->d_w + net->off_conv[2 + 2 * b]; a.bias = net->d_f + net->off_bias[2 + 2 * b];
-    if ((e = launch_conv<8, 9, 256, EPI_SKIP_RELU>(net, a, stream)) != cudaSuccess) return e;   // x = relu(x + f(x)), in place
+    a.in = act.d_x; a.out = act.d_y; a.w = net->d_w + net->off_conv[1 + 2 * b]; a.bias = net->d_f + net->off_bias[1 + 2 * b];
+    if ((e = launch_conv<8, 9, 256, EPI_RELU>(act, a, stream)) != cudaSuccess) return e;
+    a.in = act.d_y; a.out = act.d_x; a.w = net->d_w + net->off_conv[2 + 2 * b]; a.bias = net->d_f + net->off_bias[2 + 2 * b];
+    // x = relu(x + f(x)), in place; the last block's epilogue also forms the value head's 1x1 conv
+    if (b + 1 < NET_BLOCKS) e = launch_conv<8, 9, 256, EPI_SKIP_RELU>(act, a, stream);
+    else { a.vw = net->d_f + net->off_vw; a.vcell = act.d_vcell; e = launch_conv<8, 9, 256, EPI_SKIP_RELU_VALUE>(act, a, stream); }
+    if (e != cudaSuccess) return e;
     n += 2;
   }
   // policy head: y = relu(conv1x1(x)); logits = conv1x1(y)
-  a.in = net->d_x; a.out = net->d_y; a.w = net->d_w + net->off_p1; a.bias = net->d_f + net->off_bp1;
-  if ((e = launch_conv<8, 1, 256, EPI_RELU>(net, a, stream)) != cudaSuccess) return e;
-  a.in = net->d_y; a.out = nullptr; a.w = net->d_w + net->off_p2; a.bias = net->d_f + net->off_bp2;
-  if ((e = launch_conv<8, 1, 80, EPI_LOGITS>(net, a, stream)) != cudaSuccess) return e;
+  a.in = act.d_x; a.out = act.d_y; a.w = net->d_w + net->off_p1; a.bias = net->d_f + net->off_bp1;
+  if ((e = launch_conv<8, 1, 256, EPI_RELU>(act, a, stream)) != cudaSuccess) return e;
+  a.in = act.d_y; a.out = nullptr; a.w = net->d_w + net->off_p2; a.bias = net->d_f + net->off_bp2;
+  if ((e = launch_conv<8, 1, 80, EPI_LOGITS>(act, a, stream)) != cudaSuccess) return e;
   n += 2;
-  k_value_head<<<net->max_positions, 256, 0, stream>>>(net->d_x, plane_rows, list, count_dev, net->d_f + net->off_vw, net->d_f + net->off_vb,
-                                                       net->d_f + net->off_f1w, net->d_f + net->off_f1b, net->d_f + net->off_f2w,
-                                                       net->d_f + net->off_f2b, values);
+  k_value_head<<<(act.max_positions + VH_POS - 1) / VH_POS, 256, 0, stream>>>(act.d_vcell, list, count_dev, net->d_f + net->off_vb, net->d_f + net->off_f1w,
+                                                                              net->d_f + net->off_f1b, net->d_f + net->off_f2w, net->d_f + net->off_f2b, values);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   ++n;
   if (launched) *launched = n;
@@ -524,14 +563,15 @@ cudaError_t net_forward(Net* net, const Pos* pos, const uint32_t* reps, const ui
 // Re-runs one residual convolution (k_conv<8, 9, 256, EPI_RELU>: x -> y, layer 1; y is scratch between blocks) on the
 // activations the last forward left in HBM, `iters` launches between two CUDA events on `stream`.
 cudaError_t net_time_conv(Net* net, const uint32_t* count_dev, uint32_t iters, cudaStream_t stream, cudaEvent_t ev0, cudaEvent_t ev1, float* avg_ms) {
+  const ActSet& act = net->act[0];
   ConvArgs a{};
-  a.count = count_dev; a.plane_rows = (uint32_t)net->plane_rows;
-  a.in = net->d_x; a.out = net->d_y; a.w = net->d_w + net->off_conv[1]; a.bias = net->d_f + net->off_bias[1];
+  a.count = count_dev; a.plane_rows = (uint32_t)act.plane_rows;
+  a.in = act.d_x; a.out = act.d_y; a.w = net->d_w + net->off_conv[1]; a.bias = net->d_f + net->off_bias[1];
   cudaError_t e;
-  if ((e = launch_conv<8, 9, 256, EPI_RELU>(net, a, stream)) != cudaSuccess) return e;   // warm
+  if ((e = launch_conv<8, 9, 256, EPI_RELU>(act, a, stream)) != cudaSuccess) return e;   // warm
   if ((e = cudaEventRecord(ev0, stream)) != cudaSuccess) return e;
   for (uint32_t i = 0; i < iters; ++i)
-    if ((e = launch_conv<8, 9, 256, EPI_RELU>(net, a, stream)) != cudaSuccess) return e;
+    if ((e = launch_conv<8, 9, 256, EPI_RELU>(act, a, stream)) != cudaSuccess) return e;
   if ((e = cudaEventRecord(ev1, stream)) != cudaSuccess) return e;
   if ((e = cudaEventSynchronize(ev1)) != cudaSuccess) return e;
   float ms = 0.f;
@@ -540,9 +580,8 @@ cudaError_t net_time_conv(Net* net, const uint32_t* count_dev, uint32_t iters, c
   return cudaSuccess;
 }
 
-int32_t net_forward_leaves(spb_chess_engine* e, uint32_t* launched) {
-  const cudaError_t ce = net_forward(e->net, e->T.leaf_pos, e->T.leaf_reps, e->T.eval_list, e->T.eval_count, e->T.eval_logits, e->T.eval_value,
-                                     e->stream, launched);
+int32_t net_forward_leaves(spb_chess_engine* e, int set, const uint32_t* list, const uint32_t* count_dev, cudaStream_t stream, uint32_t* launched) {
+  const cudaError_t ce = net_forward(e->net, set, e->T.leaf_pos, e->T.leaf_reps, list, count_dev, e->T.eval_logits, e->T.eval_value, stream, launched);
   if (ce != cudaSuccess) { e->set_error(std::string("chess network launch: ") + cudaGetErrorString(ce)); return SPB_ERR_CUDA; }
   return SPB_OK;
 }
@@ -683,7 +722,7 @@ int32_t spb_chess_predict(spb_chess_engine* e, const spb_chess_state* states, co
   ch::k_predict_prepare<<<(n + 3) / 4, 128, 0, e->stream>>>(d_states, d_hist, n, d_moves, d_nmoves, d_reps, e->T.error);
   CH_CUDA(e, cudaGetLastError());
   uint32_t launched = 0;
-  const cudaError_t ce = ch::net_forward(e->net, d_states, d_reps, nullptr, d_count, d_logits, d_values, e->stream, &launched);
+  const cudaError_t ce = ch::net_forward(e->net, 0, d_states, d_reps, nullptr, d_count, d_logits, d_values, e->stream, &launched);
   if (ce != cudaSuccess) { e->set_error(std::string("chess network launch: ") + cudaGetErrorString(ce)); return SPB_ERR_CUDA; }
   e->launches += 1 + launched;
   if (policies) {

@@ -43,12 +43,13 @@ bool net_loaded(const Net* net);
 double net_flops_per_position();
 
 // Evaluates pos[list[i]] (repetition count reps[list[i]] for plane 16) for i < *count_dev (read on the device, at most the
-// net's max_positions) and writes logits[list[i]][4672] (raw, f32) and values[list[i]] (tanh).  list == nullptr: identity.
-cudaError_t net_forward(Net* net, const Pos* pos, const uint32_t* reps, const uint32_t* list, const uint32_t* count_dev, float* logits,
+// capacity of activation set `set`: 0 = max_positions, 1 = half of it) and writes logits[list[i]][4672] (raw, f32) and values[list[i]] (tanh).  list == nullptr: identity.
+cudaError_t net_forward(Net* net, int set, const Pos* pos, const uint32_t* reps, const uint32_t* list, const uint32_t* count_dev, float* logits,
                         float* values, cudaStream_t stream, uint32_t* launched);
 cudaError_t net_time_conv(Net* net, const uint32_t* count_dev, uint32_t iters, cudaStream_t stream, cudaEvent_t ev0, cudaEvent_t ev1, float* avg_ms);
-// the evaluator step of the lock-step search: the pending leaves of e->T
-int32_t net_forward_leaves(spb_chess_engine* e, uint32_t* launched);
+// the evaluator step of the lock-step search: the pending leaves of one range of e->T's trees (work list `list`, its length on
+// the device), in activation set `set`, on `stream`
+int32_t net_forward_leaves(spb_chess_engine* e, int set, const uint32_t* list, const uint32_t* count_dev, cudaStream_t stream, uint32_t* launched);
 
 }  // namespace chess
 }  // namespace spb
