@@ -555,7 +555,7 @@ def run_chess(args):
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": chess_workload(G, sims), "games_per_gpu": G, "sims_per_move": sims, "leaves_per_tree": 1,
-                   "pipeline": "lock-step (the reference's loop: select over all trees, one network batch, expand + backup)",
+                   "pipeline": "lock-step (the reference's loop: select, one network batch, expand + backup), run as two half-loops over the two halves of the trees on two streams",
                    "evaluator": "chess 10x256 conv ResNet, random init (numpy seed 0), BN folded, bf16 operands / f32 accumulate",
                    "roots": "seeded random playouts of 0..%d plies from the start position (device rules)" % (CHESS_MAX_PLY - 1),
                    "parallelism": "games sharded by rank, no collective on the search path",
@@ -570,7 +570,7 @@ def run_chess(args):
                      "kernel": "chess::k_conv<8, 9, 256> (one 256->256 3x3 residual convolution over the leaf batch; 20 of the 25 launches "
                                "per evaluation and 99 % of its FLOPs)",
                      "peak_source": peak_src, "positions_per_launch": conv_n, "flops_per_launch": conv_flops, "avg_launch_ms": conv_ms,
-                     "useful_row_fraction": 64.0 / 81.0,
+                     "useful_row_fraction": 64.0 / 72.0,   # an M tile is 16 board rows of 8 cells: 8 of 9 board rows of a position are real
                      "whole_network": {"flops_per_position": flops_pos,
                                        "tflops_over_search": flops_pos * evals / (dev_ms * 1e-3) / 1e12,
                                        "note": "all evaluations x FLOPs per evaluation / device time of the searches (tree kernels included)"}},

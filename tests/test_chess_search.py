@@ -396,6 +396,30 @@ def test_chess_network_search_matches_oracle_with_torch_evaluator(chess_net):
             assert np.allclose(pri, pri_ref, rtol=5 * RTOL, atol=1e-4), i
 
 
+@pytest.mark.gpu
+def test_chess_network_pipeline_two_half_loops_equal_one_loop(chess_net):
+    """From 256 trees on, the network pipeline runs the two halves of the trees as two lock-step loops on two streams (tree
+    kernels of one half under the convolutions of the other).  Trees never interact, so every tree must come out exactly as
+    from one loop over all trees (SPB_FLAG_LOCKSTEP); 301 trees: an odd split, a ragged last tile."""
+    from oracle import torch_net
+    from selfplay_b200.synth import synthetic_chess_roots_device
+    blob = torch_net.chess_to_safetensors_explicit(chess_net)
+    out = []
+    for flags in (0, S.FLAG_LOCKSTEP):
+        with S.ChessEngine(num_games=301, evaluator=S.EVAL_NET, flags=flags) as e:
+            e.load_weights(blob)
+            st, hist = synthetic_chess_roots_device(e, 301)
+            e.reset_games(st, hist)
+            e.search(20)
+            mv, cnt, ids, n = e.root_children_all()
+            out.append((mv.copy(), cnt.copy(), ids.copy(), n.copy(), e.counters()))
+    for a, b in zip(out[0][:4], out[1][:4]):
+        assert (a == b).all()
+    for k in ("simulations", "evaluations", "terminal_leaves"):
+        assert out[0][4][k] == out[1][4][k], k
+    assert (out[0][1].sum(axis=1)[out[0][3] > 0] == 19).all()   # 19 visits below every non-terminal root
+
+
 # ---- GPU: the kernels of the network pipeline under the deterministic evaluators, and the full size of configs[4] --------
 
 @pytest.mark.gpu
