@@ -62,12 +62,16 @@ def metric_name(game, sims):
         "Connect4" if game == "c4" else "tic-tac-toe", sims)
 
 
-def ncu_traffic():
+NCU_SUMMARY_CHESS = os.path.join("profiles", "r02_ncu_chess_conv_summary.json")   # k_conv<8,9,256> over 2,048 positions
+
+
+def ncu_traffic(summary=None):
     """DRAM bytes (read + write) per launch of the dominant kernel, from the committed `ncu --set full` summary."""
+    summary = summary or NCU_SUMMARY
     try:
-        with open(os.path.join(ROOT, NCU_SUMMARY)) as f:
+        with open(os.path.join(ROOT, summary)) as f:
             j = json.load(f)
-        return j.get("traffic_bytes_per_launch"), NCU_SUMMARY
+        return j.get("traffic_bytes_per_launch"), summary
     except Exception:
         return None, None
 
@@ -566,7 +570,9 @@ def run_chess(args):
                 "d2h_bytes_per_step": int(mv.nbytes + cnt.nbytes + ids.nbytes + ncs.nbytes)},
         "gpu_launches": int(ctr["kernel_launches"]),
         "clocks": clocks,
-        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None,
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                     "traffic": ncu_traffic(NCU_SUMMARY_CHESS)[0] if conv_n == 2048 else None,
+                     "traffic_source": NCU_SUMMARY_CHESS if conv_n == 2048 else None,
                      "kernel": "chess::k_conv<8, 9, 256> (one 256->256 3x3 residual convolution over the leaf batch; 20 of the 25 launches "
                                "per evaluation and 99 % of its FLOPs)",
                      "peak_source": peak_src, "positions_per_launch": conv_n, "flops_per_launch": conv_flops, "avg_launch_ms": conv_ms,
