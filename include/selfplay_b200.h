@@ -100,7 +100,8 @@ typedef struct spb_config {
 #define SPB_FLAG_EVAL_SIMT  2u   /* use the CUDA-core evaluator kernel instead of tcgen05 (debug / cross-check) */
 #define SPB_FLAG_LOCKSTEP   32u  /* network evaluator: run the reference's loop literally — per simulation step one evaluator
                                     launch for the leaves of all trees, then one tree-step launch (mcts.rs:214-286) — instead of
-                                    the asynchronous pipeline, whose results are bit-identical */
+                                    the asynchronous pipeline, whose results are bit-identical.  Chess engine:
+                                    one lock-step loop over all trees instead of two half-loops on two streams */
 #define SPB_FLAG_FIXED_POOL 16u  /* never grow the node pools: a tree that would pass max_nodes_per_tree makes spb_search return
                                     SPB_ERR_POOL.  Without the flag the pools grow before a search that could outgrow them, like
                                     the reference's Vec arena (mcts.rs:19) */
