@@ -24,7 +24,8 @@
 // early) and F (columns 128..191, left tap, one row late).  12 MMAs per tile-layer instead of 36; the epilogue forms
 // out[r] = D[r] + E[r+1] + F[r-1] with two warp shuffles per channel — rows 32k-1 are pad cells, so lane 31 never needs
 // E of the next warp and lane 0 takes F = 0 (F of a pad-column row is a sum over pad-column cells, which are zero).
-// The stem (one K step) and the fused head conv (N = 3 x 48) have the same form.  Accumulators: two sets of 192 TMEM
+// The fused head conv (N = 3 x 48) has the same form; the stem (one K step, 3 input planes) issues nine N = 64 MMAs, one per
+// tap, into one accumulator: its epilogue needs no shuffles, and its phase is paced by the epilogue warps, not the tensor pipe.  Accumulators: two sets of 192 TMEM
 // columns used in rotation by the CTA's tile sequence (batch, layer, tile); the spare 2 x 64 columns carry the skip
 // connection of the residual blocks from the epilogue that produced it to the epilogue that adds it.
 #include <cuda_bf16.h>
@@ -87,10 +88,20 @@ static void pack_t(const HostNet& net, std::vector<uint8_t>* out) {
   using Ge = Geo<G>;
   out->assign(image_bytes<G>(), 0);
   uint8_t* img = out->data();
-  // Every conv layer in the kx-triple form: per kernel row ky one block [KC chunks][3N n][8] bf16 whose B rows are the
+  // Every conv layer but the stem in the kx-triple form: per kernel row ky one block [KC chunks][3N n][8] bf16 whose B rows are the
   // centre tap (n < N), the right tap (N <= n < 2N) and the left tap (2N <= n < 3N) of that kernel row — one MMA of
   // width 3N per K step serves all three taps from ONE fetch of A.  3 blocks per layer = the 3 ring groups.
-  for (int l = 0; l < N_LAYERS; ++l) {
+  // The stem (K = 16: one K step) keeps one block [2 chunks][64 n][8] per tap, tap = ky*3 + kx: its 9 small MMAs cost the
+  // tensor pipe nothing where it runs (behind the head conv of the previous batch, whose phase is paced by the epilogue
+  // warps), and its epilogue needs no shuffles.
+  for (int tap = 0; tap < 9; ++tap) {
+    const HostNet::Conv& cv = net.conv[0];
+    uint16_t* blk = reinterpret_cast<uint16_t*>(img + layer_offset(0) + (size_t)tap * layer_tap_bytes(0));
+    for (int n = 0; n < 64; ++n)
+      for (int k = 0; k < 16 && k < cv.ic; ++k)
+        blk[((size_t)(k / 8) * 64 + n) * 8 + (k % 8)] = f2bf(cv.w[((size_t)n * cv.ic + k) * 9 + tap]);   // [OC][IC][ky][kx]
+  }
+  for (int l = 1; l < N_LAYERS; ++l) {
     const int N = layer_n(l), KC = layer_kchunks(l);
     const int n_real = l == 9 ? NET_POLICY_CH + NET_VALUE_CH : 64;
     for (int ky = 0; ky < 3; ++ky) {
@@ -162,6 +173,32 @@ __device__ __forceinline__ void issue_tile_triple(bool issuer, uint32_t a_lo_til
         umma_f16(d_tmem, ((uint64_t)DESC_HI << 32) | a_lo, ((uint64_t)DESC_HI << 32) | b_lo, IDESC, (ky | kk) != 0);
       }
       if (last_tile) umma_commit(bar_base + (uint32_t)(N_SLOTS + ky) * 8u);                        // w_empty[ky]
+    }
+    __syncwarp();
+  }
+}
+
+// The stem: one N = 64 MMA per tap (K = 16 is one K step), A shifted by the tap's row offset, all nine accumulating in D.
+// Ring group ky holds the taps 3 ky .. 3 ky + 2 (2 KB each).
+template <int W8, int Q>
+__device__ __forceinline__ void issue_tile_stem(bool issuer, uint32_t a_lo_tile, uint32_t b_lo_base, uint32_t d_tmem, bool first_tile,
+                                                bool last_tile, uint32_t w_par, uint32_t bar_base) {
+  constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);
+  constexpr uint32_t IDESC = make_idesc(64);
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky) {
+    if (first_tile) {
+      mbar_wait(bar_base + (uint32_t)ky * 8u, w_par);
+      tc_fence_after();
+    }
+    if (issuer) {
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const uint32_t a_lo = a_lo_tile + (uint32_t)((ky - 1) * W8 + (kx - 1));
+        const uint32_t b_lo = (b_lo_base + (uint32_t)(3 * ky) * (SLOT_BYTES >> 4) + (uint32_t)kx * (2048u >> 4)) | (64u << 16);
+        umma_f16(d_tmem, ((uint64_t)DESC_HI << 32) | a_lo, ((uint64_t)DESC_HI << 32) | b_lo, IDESC, (ky | kx) != 0);
+      }
+      if (last_tile) umma_commit(bar_base + (uint32_t)(N_SLOTS + ky) * 8u);
     }
     __syncwarp();
   }
@@ -394,7 +431,7 @@ k_eval_umma(const uint8_t* __restrict__ image, const EvalWork W, const Trees T, 
             const uint32_t d_tmem = tmem_base + set * 256u;
             const bool first = (t == 0), last = (t == nt - 1);
             if (l == 0)
-              issue_tile_triple<Ge::W8, Ge::Q, 1, 192>(issuer, a_lo_tile, b_lo_base, d_tmem, first, last, use & 1u, bar_base, 0u, 0u);
+              issue_tile_stem<Ge::W8, Ge::Q>(issuer, a_lo_tile, b_lo_base, d_tmem, first, last, use & 1u, bar_base);
             else if (l < 9)
               issue_tile_triple<Ge::W8, Ge::Q, 4, 192>(issuer, a_lo_tile, b_lo_base, d_tmem, first, last, use & 1u, bar_base, mid_bar, mid_par);
             else
@@ -530,10 +567,12 @@ k_eval_umma(const uint8_t* __restrict__ image, const EvalWork W, const Trees T, 
         uint32_t a[32], e[32], f[32];
         tmem_ld16(taddr, a);
         tmem_ld16(taddr + 16u, a + 16);
-        tmem_ld16(taddr + 64u, e);
-        tmem_ld16(taddr + 80u, e + 16);
-        tmem_ld16(taddr + 128u, f);
-        tmem_ld16(taddr + 144u, f + 16);
+        if (l != 0) {                                                // the stem accumulates all nine taps in D
+          tmem_ld16(taddr + 64u, e);
+          tmem_ld16(taddr + 80u, e + 16);
+          tmem_ld16(taddr + 128u, f);
+          tmem_ld16(taddr + 144u, f + 16);
+        }
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
@@ -542,6 +581,7 @@ k_eval_umma(const uint8_t* __restrict__ image, const EvalWork W, const Trees T, 
         float v[32];
 #pragma unroll
         for (int q = 0; q < 32; q += 2) {                           // packed f32x2 adds: two channels per instruction
+          if (l == 0) { v[q] = __uint_as_float(a[q]); v[q + 1] = __uint_as_float(a[q + 1]); continue; }
           const float e0 = __uint_as_float(__shfl_down_sync(0xffffffffu, e[q], 1)), e1 = __uint_as_float(__shfl_down_sync(0xffffffffu, e[q + 1], 1));
           const float f0 = __uint_as_float(__shfl_up_sync(0xffffffffu, f[q], 1)), f1 = __uint_as_float(__shfl_up_sync(0xffffffffu, f[q + 1], 1));
           v[q] = __uint_as_float(a[q]); v[q + 1] = __uint_as_float(a[q + 1]);
