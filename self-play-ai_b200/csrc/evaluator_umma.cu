@@ -371,7 +371,7 @@ k_eval_umma(const uint8_t* __restrict__ image, const EvalWork W, const Trees T, 
 #define SPB_REGS_EPILOGUE() do { if (RING) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_EPILOGUE)); } while (0)
 
   if (warp == PRODUCER_WARP) {
-    // ===== weight producer: streams (layer, tap) blocks into the 9-slot ring ==========================
+    // ===== weight producer: streams the layers' kernel-row blocks into the 3-group ring ==================
     SPB_REGS_LIGHT();
     if (lane == 0) {
       uint32_t use = 0;                                           // completed fills of every slot

@@ -8,7 +8,7 @@
 
 namespace spb {
 namespace umma {
-// Packs the folded net into the device image the kernel streams with cp.async.bulk (UMMA operand layout, kx-pair form).
+// Packs the folded net into the device image the kernel streams with cp.async.bulk (UMMA operand layout: kx-triple blocks per kernel row, one block per tap for the stem).
 void pack_weights(const HostNet& net, std::vector<uint8_t>* out);
 // Static work list (spb_predict, lock-step pipeline).  overlap: programmatic dependent launch (set-up may run under the
 // previous kernel of the stream).

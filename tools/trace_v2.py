@@ -1,4 +1,4 @@
-"""Timeline of CTA 0 of the kx-pair evaluator (profile build): when the MMA warp issues each (batch, layer, tile) and when
+"""Timeline of CTA 0 of the evaluator on a static list (profile build): when the MMA warp issues each (batch, layer, tile) and when
 the epilogue handles it.  SPB_LIB=variants/lib_prof.so python tools/trace_v2.py"""
 import sys, os, ctypes as C
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
