@@ -848,12 +848,12 @@ k_eval_umma(const uint8_t* __restrict__ image, const EvalWork W, const Trees T, 
       if (et == 0) s_nb[4] = mbar_test(bar_batch(b + 1), ((b + 1) >> 1) & 1u) ? s_nb[(b + 1) & 3u] : NOT_YET;
       epi_bar_sync();                                               // every head activation of the batch is in shared memory
       uint32_t nb_next = s_nb[4];
-      float w_heads[8][8];                                          // loaded after the stem epilogue: 64 more live registers there would spill
+      float w_heads[8][8];
       if (nb_next != NOT_YET) {
         // The stem of the next batch ran on the tensor pipe behind this batch's head conv (the stager had its input
         // ready): release layer 1 of the next batch before spending time on this batch's Linear layers.
+        load_head_weights(w_heads, 0);                              // in flight under the stem's (light: one accumulator, no shuffles) epilogue
         if (nb_next != 0u) conv_epilogue(b + 1, 0);
-        load_head_weights(w_heads, 0);
         if (NOUT <= 8 && nb_next != 0u) {
           // Only the board loop reads the head activations in buffer 0, which layer 1's epilogue overwrites: the reduction,
           // softmax and hand-off to the publisher follow layer 1 of the next batch, whose MMAs would otherwise wait for them
