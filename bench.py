@@ -15,7 +15,8 @@ fixed (weak scaling); `value` is the whole-job aggregate.
   value     sims/s with the roots already resident in HBM; device time (CUDA events on the engine's stream),
             max over ranks.
   e2e       the same metric through the C ABI with HOST buffers: spb_reset_games (H2D) + spb_search +
-            spb_root_children_all (D2H) per step, wall clock between synchronisations, max over ranks.
+            spb_root_children_all (D2H) per step, wall clock between synchronisations, max over ranks.  The K value steps
+            and the K e2e steps alternate, so that both are measured in the same power state of the board.
   roofline  the dominant kernel.  Default (asynchronous pipeline): ONE resident kernel per search that holds the tcgen05
             evaluator and the tree warps; achieved = evaluated positions x FLOPs per position / the search's device time
             (CUDA events on the engine's stream), against the measured sustained bf16 peak of MEASURED_PEAKS.json.
@@ -280,34 +281,37 @@ def run_ours(args):
         eng.search(sims)
         eng.root_children_all()
 
-    # ---- timed region 1: device-resident (`value`) ---------------------------------------------------
+    # ---- timed regions: device-resident (`value`) and end to end through the C ABI with host buffers (`e2e`) ----------
+    # K steps each, ALTERNATING (value step, e2e step, value step, ...): the board sits at its power cap and its clocks drift
+    # over seconds, so two loops run one after the other would be measured in two different power states.  `value` sums
+    # the device time of its K searches (CUDA events on the engine stream inside spb_search); `e2e` sums the wall time of
+    # its K steps, each = H2D of the step's inputs + search + D2H of the step's result (synchronous calls).
     sampler = ClockSampler(local_rank)
     sampler.start()
-    eng.reset_counters()
+    ADDITIVE = ("simulations", "evaluations", "terminal_leaves", "path_length_sum", "children_created", "kernel_launches")
+    ctr, stats = None, None
     barrier()
-    dev_ms, t0 = 0.0, time.perf_counter()
-    stats = None
+    dev_ms, wall_s, e2e_s = 0.0, 0.0, 0.0
     for _ in range(args.steps):
+        eng.reset_counters()
+        t0 = time.perf_counter()
         eng.reset_games(roots)            # untimed part of `value`: fresh trees; roots then live in HBM
         eng.search(sims)                  # synchronous; its device time is measured with CUDA events inside
+        wall_s += time.perf_counter() - t0
         dev_ms += eng.last_search_timing()[0]
-    barrier()
-    wall_s = time.perf_counter() - t0
-    ctr = eng.counters()
-    stats = eng.async_stats()
-    launches = ctr["kernel_launches"]
-    dev_ms = rank_max(dev_ms)
-    wall_s = rank_max(wall_s)
-
-    # ---- timed region 2: end to end through the C ABI with host buffers (`e2e`) ----------------------
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
+        c = eng.counters()
+        ctr = c if ctr is None else {k: (ctr[k] + c[k] if k in ADDITIVE else c[k]) for k in c}
+        stats, stats_ms = eng.async_stats(), eng.last_search_timing()[0]
+        t0 = time.perf_counter()
         eng.reset_games(roots)            # H2D of the step's inputs
         eng.search(sims)
         acts, counts, ids, ncs = eng.root_children_all()   # D2H of the step's result
+        e2e_s += time.perf_counter() - t0
     barrier()
-    e2e_s = rank_max(time.perf_counter() - t0)
+    launches = ctr["kernel_launches"]
+    dev_ms = rank_max(dev_ms)
+    wall_s = rank_max(wall_s)
+    e2e_s = rank_max(e2e_s)
     clocks = sampler.stop()
     h2d = G * 16
     d2h = G * (2 * 4 * S.MAX_ACTIONS + 4 + S.MAX_ACTIONS)
@@ -349,14 +353,14 @@ def run_ours(args):
                    "evaluator": "%s 4x64 conv ResNet, random init (numpy seed 0), BN folded" % ("connect4" if args.game == "c4" else "tic-tac-toe"),
                    "parallelism": "games sharded by rank, no collective on the search path",
                    "cache": "inputs larger than L2: per-GPU node pools touched per step ~%d MB" % (ctr["nodes_live"] * 20 // (1 << 20)),
-                   "timing": "CUDA events on the engine stream around each search, max over ranks; wall clock %.3f s" % wall_s},
+                   "timing": "CUDA events on the engine stream around each search, max over ranks; wall clock %.3f s; value and e2e steps alternate (same power state)" % wall_s},
         "e2e": {"value": total_sims / e2e_s, "unit": "sims/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roof,
         "tree_side": {"bytes_per_sim_algorithmic": tree_bytes_per_sim, "mean_path_length": D, "mean_branching": bbar,
                       "algorithmic_gbs": tree_bytes_per_sim * G * sims * args.steps / (dev_ms * 1e-3) / 1e9, "hbm_peak_gbs": peak_hbm,
-                      "tree_warps": stats["tree_warps"], "tree_warp_busy_frac": stats["tree_busy_ns"] / max(1, stats["tree_warps"]) / max(1e-9, eng.last_search_timing()[0] * 1e6),
+                      "tree_warps": stats["tree_warps"], "tree_warp_busy_frac": stats["tree_busy_ns"] / max(1, stats["tree_warps"]) / max(1e-9, stats_ms * 1e6),
                       "us_per_tree_visit": stats["tree_busy_ns"] / max(1, stats["tree_visits"]) / 1e3,
                       "boards_per_evaluator_batch": stats["boards"] / max(1, stats["batches"]),
                       "note": "latency-bound pointer chasing that runs under the evaluator in the same kernel; statistics of the last search (spb_last_async_stats)"},
@@ -528,25 +532,28 @@ def run_chess(args):
         eng.root_children_all()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    eng.reset_counters()
+    ADDITIVE = ("simulations", "evaluations", "terminal_leaves", "path_length_sum", "children_created", "kernel_launches")
+    ctr = None
     barrier()
-    dev_ms, t0 = 0.0, time.perf_counter()
-    for _ in range(args.steps):
+    dev_ms, wall_s, e2e_s = 0.0, 0.0, 0.0
+    for _ in range(args.steps):           # value step, e2e step, value step, ...: both measured in the same power state
+        eng.reset_counters()
+        t0 = time.perf_counter()
         eng.reset_games(roots, hist)
         eng.search(sims)
+        wall_s += time.perf_counter() - t0
         dev_ms += eng.last_search_ms()
-    barrier()
-    wall_s = rank_max(time.perf_counter() - t0)
-    ctr = eng.counters()
-    dev_ms = rank_max(dev_ms)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
+        c = eng.counters()
+        ctr = c if ctr is None else {k: (ctr[k] + c[k] if k in ADDITIVE else c[k]) for k in c}
+        t0 = time.perf_counter()
         eng.reset_games(roots, hist)                        # H2D: states + game histories
         eng.search(sims)
         mv, cnt, ids, ncs = eng.root_children_all()         # D2H: moves, visit counts, child ids
+        e2e_s += time.perf_counter() - t0
     barrier()
-    e2e_s = rank_max(time.perf_counter() - t0)
+    wall_s = rank_max(wall_s)
+    dev_ms = rank_max(dev_ms)
+    e2e_s = rank_max(e2e_s)
     clocks = sampler.stop()
     assert int(cnt[0].sum()) == sims - 1
     peak_tf, peak_hbm, peak_src = _peaks()
@@ -565,7 +572,7 @@ def run_chess(args):
                    "parallelism": "games sharded by rank, no collective on the search path",
                    "cache": "inputs larger than L2: activations of one layer %d MB, node pools touched ~%d MB" % (
                        G * 81 * 512 // (1 << 20), ctr["nodes_live"] * 32 // (1 << 20)),
-                   "timing": "CUDA events on the engine stream around each search, max over ranks; wall clock %.3f s" % wall_s},
+                   "timing": "CUDA events on the engine stream around each search, max over ranks; wall clock %.3f s; value and e2e steps alternate (same power state)" % wall_s},
         "e2e": {"value": total_sims / e2e_s, "unit": "sims/s", "h2d_bytes_per_step": int(roots.nbytes + hist.nbytes),
                 "d2h_bytes_per_step": int(mv.nbytes + cnt.nbytes + ids.nbytes + ncs.nbytes)},
         "gpu_launches": int(ctr["kernel_launches"]),
