@@ -15,7 +15,8 @@ fixed (weak scaling); `value` is the whole-job aggregate.
   value     sims/s with the roots already resident in HBM; device time (CUDA events on the engine's stream),
             max over ranks.
   e2e       the same metric through the C ABI with HOST buffers: spb_reset_games (H2D) + spb_search +
-            spb_root_children_all (D2H) per step, wall clock between synchronisations, max over ranks.  The K value steps
+            spb_root_children_all (D2H) per step, page-locked host buffers allocated once, wall clock between
+            synchronisations, max over ranks.  The K value steps
             and the K e2e steps alternate, so that both are measured in the same power state of the board.
   roofline  the dominant kernel.  Default (asynchronous pipeline): ONE resident kernel per search that holds the tcgen05
             evaluator and the tree warps; achieved = evaluated positions x FLOPs per position / the search's device time
@@ -64,6 +65,21 @@ def metric_name(game, sims):
 
 
 NCU_SUMMARY_CHESS = os.path.join("profiles", "r02_ncu_chess_conv_summary.json")   # k_conv<8,9,256> over 2,048 positions
+
+
+def pinned(arr):
+    """A copy of `arr` in page-locked host memory (the e2e steps copy their inputs from / their results to pinned buffers)."""
+    import numpy as np
+    import torch
+    t = torch.empty(max(1, arr.nbytes), dtype=torch.uint8, pin_memory=True)
+    out = t.numpy()[:arr.nbytes].view(arr.dtype).reshape(arr.shape)
+    out[...] = arr
+    out.flags.writeable = True
+    _PINNED_KEEPALIVE.append(t)
+    return out
+
+
+_PINNED_KEEPALIVE = []
 
 
 def ncu_traffic(summary=None):
@@ -276,10 +292,12 @@ def run_ours(args):
         return float(t.item())
 
     # ---- warm-up ------------------------------------------------------------------------------------
+    roots = pinned(roots)                 # host buffers of the e2e steps: page-locked, allocated once
+    out_bufs = tuple(pinned(x) for x in eng.root_children_all())
     for _ in range(args.warmup):
         eng.reset_games(roots)
         eng.search(sims)
-        eng.root_children_all()
+        eng.root_children_all(out_bufs)
 
     # ---- timed regions: device-resident (`value`) and end to end through the C ABI with host buffers (`e2e`) ----------
     # K steps each, ALTERNATING (value step, e2e step, value step, ...): the board sits at its power cap and its clocks drift
@@ -305,7 +323,7 @@ def run_ours(args):
         t0 = time.perf_counter()
         eng.reset_games(roots)            # H2D of the step's inputs
         eng.search(sims)
-        acts, counts, ids, ncs = eng.root_children_all()   # D2H of the step's result
+        acts, counts, ids, ncs = eng.root_children_all(out_bufs)   # D2H of the step's result
         e2e_s += time.perf_counter() - t0
     barrier()
     launches = ctr["kernel_launches"]
@@ -526,10 +544,12 @@ def run_chess(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    roots, hist = pinned(roots), pinned(hist)   # host buffers of the e2e steps: page-locked, allocated once
+    out_bufs = tuple(pinned(x) for x in eng.root_children_all())
     for _ in range(args.warmup):
         eng.reset_games(roots, hist)
         eng.search(sims)
-        eng.root_children_all()
+        eng.root_children_all(out_bufs)
     sampler = ClockSampler(local_rank)
     sampler.start()
     ADDITIVE = ("simulations", "evaluations", "terminal_leaves", "path_length_sum", "children_created", "kernel_launches")
@@ -548,7 +568,7 @@ def run_chess(args):
         t0 = time.perf_counter()
         eng.reset_games(roots, hist)                        # H2D: states + game histories
         eng.search(sims)
-        mv, cnt, ids, ncs = eng.root_children_all()         # D2H: moves, visit counts, child ids
+        mv, cnt, ids, ncs = eng.root_children_all(out_bufs)   # D2H: moves, visit counts, child ids
         e2e_s += time.perf_counter() - t0
     barrier()
     wall_s = rank_max(wall_s)

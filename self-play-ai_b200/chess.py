@@ -174,11 +174,17 @@ class ChessEngine:
         k = n.value
         return mv[:k].tolist(), cnt[:k].tolist(), ids[:k].tolist()
 
-    def root_children_all(self):
-        mv = np.zeros((self.G, MAX_MOVES), np.uint16)
-        cnt = np.zeros((self.G, MAX_MOVES), np.uint32)
-        ids = np.zeros((self.G, MAX_MOVES), np.uint32)
-        n = np.zeros(self.G, np.uint32)
+    def root_children_all(self, out=None):
+        """`out`: the four arrays of an earlier call (e.g. in pinned host memory), written in place."""
+        if out is not None:
+            mv, cnt, ids, n = out
+            assert mv.shape == (self.G, MAX_MOVES) and mv.dtype == np.uint16 and cnt.dtype == np.uint32 and ids.dtype == np.uint32 and n.shape == (self.G,)
+            assert all(x.flags.c_contiguous for x in out)
+        else:
+            mv = np.zeros((self.G, MAX_MOVES), np.uint16)
+            cnt = np.zeros((self.G, MAX_MOVES), np.uint32)
+            ids = np.zeros((self.G, MAX_MOVES), np.uint32)
+            n = np.zeros(self.G, np.uint32)
         self._chk(self._L.spb_chess_root_children_all(self._h, mv.ctypes.data, cnt.ctypes.data, ids.ctypes.data, n.ctypes.data))
         return mv, cnt, ids, n
 

@@ -475,6 +475,9 @@ int32_t spb_chess_create(const spb_config* cfg, spb_chess_engine** out) {
   if (!rc) rc = e->dalloc(&e->d_rc_ids, G * ch::MAX_MOVES);
   if (!rc) rc = e->dalloc(&e->d_rc_n, G);
   if (!rc) rc = e->dalloc(&e->d_misc, 4);
+  if (!rc) rc = e->dalloc(&e->d_reset_slots, G);
+  if (!rc) rc = e->dalloc(&e->d_reset_roots, G);
+  if (!rc) rc = e->dalloc(&e->d_reset_hist, G * SPB_CHESS_MAX_HISTORY);
   if (rc) return fail(rc, e->err);
   cudaMemsetAsync(T.live, 0, G, e->stream);
   cudaMemsetAsync(T.buf, 0, G, e->stream);
@@ -519,11 +522,9 @@ int32_t spb_chess_reset_games(spb_chess_engine* e, const uint32_t* slots, uint32
     CH_ARG(e, history || roots[i].hist_len == 0, "root with hist_len > 0 needs its history");
     CH_ARG(e, roots[i].hist_len <= SPB_CHESS_MAX_HISTORY, "hist_len > SPB_CHESS_MAX_HISTORY");
   }
-  ch::Scratch sc;
-  uint32_t* d_slots = slots ? sc.alloc<uint32_t>(n) : nullptr;
-  ch::Pos* d_roots = roots ? sc.alloc<ch::Pos>(n) : nullptr;
-  unsigned long long* d_hist = history ? sc.alloc<unsigned long long>((size_t)n * SPB_CHESS_MAX_HISTORY) : nullptr;
-  if ((slots && !d_slots) || (roots && !d_roots) || (history && !d_hist)) { e->set_error("chess: out of device memory"); return SPB_ERR_NOMEM; }
+  uint32_t* d_slots = slots ? e->d_reset_slots : nullptr;
+  ch::Pos* d_roots = roots ? e->d_reset_roots : nullptr;
+  unsigned long long* d_hist = history ? e->d_reset_hist : nullptr;
   if (slots) CH_CUDA(e, cudaMemcpyAsync(d_slots, slots, (size_t)n * 4, cudaMemcpyHostToDevice, e->stream));
   if (roots) CH_CUDA(e, cudaMemcpyAsync(d_roots, roots, (size_t)n * sizeof(ch::Pos), cudaMemcpyHostToDevice, e->stream));
   if (history) CH_CUDA(e, cudaMemcpyAsync(d_hist, history, (size_t)n * SPB_CHESS_MAX_HISTORY * 8, cudaMemcpyHostToDevice, e->stream));

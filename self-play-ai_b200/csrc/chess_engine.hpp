@@ -31,6 +31,8 @@ struct spb_chess_engine {
   // device scratch for results of whole-batch queries
   uint16_t* d_rc_moves = nullptr; uint32_t* d_rc_counts = nullptr; uint32_t* d_rc_ids = nullptr; uint32_t* d_rc_n = nullptr;
   unsigned long long* d_misc = nullptr;
+  // device staging of spb_chess_reset_games (allocated once: cudaMalloc / cudaFree per call would synchronise the device)
+  uint32_t* d_reset_slots = nullptr; spb::chess::Pos* d_reset_roots = nullptr; unsigned long long* d_reset_hist = nullptr;
 
   void set_error(const std::string& s) { err = s; }
   template <class T_> int32_t dalloc(T_** p, size_t count) {

@@ -281,12 +281,18 @@ class Engine:
         k = n.value
         return list(a[:k]), list(c[:k]), list(i[:k])
 
-    def root_children_all(self):
-        """-> (actions[G,9] u8, visit_counts[G,9] u32, child_ids[G,9] u32, n_children[G] u32), child order."""
-        a = np.zeros((self.G, MAX_ACTIONS), np.uint8)
-        c = np.zeros((self.G, MAX_ACTIONS), np.uint32)
-        i = np.zeros((self.G, MAX_ACTIONS), np.uint32)
-        n = np.zeros(self.G, np.uint32)
+    def root_children_all(self, out=None):
+        """-> (actions[G,9] u8, visit_counts[G,9] u32, child_ids[G,9] u32, n_children[G] u32), child order.
+        `out`: the four arrays of an earlier call (e.g. in pinned host memory), written in place."""
+        if out is not None:
+            a, c, i, n = out
+            assert a.shape == (self.G, MAX_ACTIONS) and a.dtype == np.uint8 and c.dtype == np.uint32 and i.dtype == np.uint32 and n.shape == (self.G,)
+            assert all(x.flags.c_contiguous for x in out)
+        else:
+            a = np.zeros((self.G, MAX_ACTIONS), np.uint8)
+            c = np.zeros((self.G, MAX_ACTIONS), np.uint32)
+            i = np.zeros((self.G, MAX_ACTIONS), np.uint32)
+            n = np.zeros(self.G, np.uint32)
         self._chk(self._L.spb_root_children_all(self._h, a.ctypes.data, c.ctypes.data, i.ctypes.data, n.ctypes.data))
         return a, c, i, n
 
