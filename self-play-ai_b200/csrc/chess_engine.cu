@@ -478,6 +478,8 @@ int32_t spb_chess_create(const spb_config* cfg, spb_chess_engine** out) {
   if (!rc) rc = e->dalloc(&e->d_reset_slots, G);
   if (!rc) rc = e->dalloc(&e->d_reset_roots, G);
   if (!rc) rc = e->dalloc(&e->d_reset_hist, G * SPB_CHESS_MAX_HISTORY);
+  if (!rc) rc = e->dalloc(&e->d_adv_ids, G);
+  if (!rc) rc = e->dalloc(&e->d_adv_err, G);
   if (rc) return fail(rc, e->err);
   cudaMemsetAsync(T.live, 0, G, e->stream);
   cudaMemsetAsync(T.buf, 0, G, e->stream);
@@ -665,12 +667,11 @@ int32_t spb_chess_advance(spb_chess_engine* e, const uint32_t* slots, const uint
   CH_ARG(e, child_ids && n <= e->T.G, "bad argument");
   if (n == 0) return SPB_OK;
   if (slots) for (uint32_t i = 0; i < n; ++i) CH_ARG(e, slots[i] < e->T.G, "slot out of range");
-  ch::Scratch sc;
-  uint32_t* d_slots = slots ? sc.alloc<uint32_t>(n) : nullptr;
-  uint32_t* d_ids = sc.alloc<uint32_t>(n);
-  ch::Pos* d_out = sc.alloc<ch::Pos>(n);
-  int32_t* d_err = sc.alloc<int32_t>(n);
-  if ((slots && !d_slots) || !d_ids || !d_out || !d_err) { e->set_error("chess: out of device memory"); return SPB_ERR_NOMEM; }
+  // persistent device staging (every call ends with a stream synchronisation): the per-move call of the self-play loop
+  uint32_t* d_slots = slots ? e->d_reset_slots : nullptr;
+  uint32_t* d_ids = e->d_adv_ids;
+  ch::Pos* d_out = e->d_reset_roots;
+  int32_t* d_err = e->d_adv_err;
   if (slots) CH_CUDA(e, cudaMemcpyAsync(d_slots, slots, (size_t)n * 4, cudaMemcpyHostToDevice, e->stream));
   CH_CUDA(e, cudaMemcpyAsync(d_ids, child_ids, (size_t)n * 4, cudaMemcpyHostToDevice, e->stream));
   ch::k_chess_advance<<<(n + ch::WARPS - 1) / ch::WARPS, ch::THREADS, 0, e->stream>>>(e->T, d_slots, d_ids, n, d_out, d_err);

@@ -33,6 +33,7 @@ struct spb_chess_engine {
   unsigned long long* d_misc = nullptr;
   // device staging of spb_chess_reset_games (allocated once: cudaMalloc / cudaFree per call would synchronise the device)
   uint32_t* d_reset_slots = nullptr; spb::chess::Pos* d_reset_roots = nullptr; unsigned long long* d_reset_hist = nullptr;
+  uint32_t* d_adv_ids = nullptr; int32_t* d_adv_err = nullptr;   // spb_chess_advance (with d_reset_slots / d_reset_roots)
 
   void set_error(const std::string& s) { err = s; }
   template <class T_> int32_t dalloc(T_** p, size_t count) {
