@@ -78,6 +78,39 @@ __device__ __forceinline__ void umma_commit_multicast(uint32_t bar, uint16_t mas
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
 }
 
+// ---- cta_group::2 for the residual convolutions (KC32 = 8, TAPS = 9, N = 256): the two CTAs of a pair issue ONE M = 256 MMA
+// for their two tiles.  Each CTA keeps only ITS half of every weight stage (128 of the 256 B rows, 8 KB): the tensor cores of
+// the pair read both halves, so a CTA fetches 4 KB of A + 4 KB of B per MMA from its shared memory instead of 4 + 8 KB (the
+// operand fetch sustains ~85 B/clk here; N = 256 at cta_group::1 needs 96).  The leader (rank 0) issues the MMAs; the
+// follower's MMA warp walks the same loop and forwards "my A group / my weight half has landed" to the leader's barriers.
+#ifndef SPB_CHESS_CTA2
+#define SPB_CHESS_CTA2 0
+#endif
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t cta_rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta_rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) { asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory"); }
+__device__ __forceinline__ void umma2_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}"
+               ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma2_commit_multicast(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
+}
+__host__ __device__ constexpr uint32_t make_idesc2(int N) {      // cta_group::2: M = 256 over the pair
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+}
+__host__ __device__ constexpr bool conv_cta2(int kc32, int taps, int n) { return SPB_CHESS_CTA2 && kc32 == 8 && taps == 9 && n == 256; }
+
 struct ConvArgs {
   const uint8_t* in;        // planar bf16 [KC32*4][plane_rows][8]
   uint8_t* out;             // planar bf16 [N/8][plane_rows][8] (EPI 0 / 1; EPI 1 adds the skip it reads from `out` itself)
@@ -99,26 +132,34 @@ template <int KC32, int TAPS, int N, int EPI>
 struct ConvCfg {
   static constexpr int A_CHUNKS = KC32 * 4;
   static constexpr uint32_t A_BYTES = (uint32_t)A_CHUNKS * QA * 16;
-  static constexpr uint32_t STAGE_BYTES = 4u * N * 16;
+  static constexpr bool CTA2 = conv_cta2(KC32, TAPS, N);
+  static constexpr uint32_t STAGE_BYTES = 4u * N * 16;             // one weight stage in global memory
+  static constexpr uint32_t SLOT_BYTES_B = CTA2 ? STAGE_BYTES / 2 : STAGE_BYTES;   // what a CTA keeps of it
+  static constexpr int NST = CTA2 ? 2 * NSTAGE : NSTAGE;          // ring depth: the same 128 KB either way
   static constexpr uint32_t GROUP_BYTES = 4u * QA * 16;       // one 32-channel group of the A tile
   static constexpr uint32_t OFF_B = A_BYTES;
-  static constexpr uint32_t OFF_BIAS = OFF_B + NSTAGE * STAGE_BYTES;
+  static constexpr uint32_t OFF_BIAS = OFF_B + NST * SLOT_BYTES_B;
   static constexpr uint32_t OFF_VW = OFF_BIAS + 256 * 4;
   static constexpr uint32_t OFF_BAR = OFF_VW + (EPI == 3 ? 256 * 4 : 0);
-  static constexpr uint32_t SMEM = OFF_BAR + 48 * 8;
+  static constexpr uint32_t N_BARS = 28 + 3 * NST;             // a_full/empty[8], acc_full/empty[2], b_full/empty[NSTAGE], peer_a_full[8], peer_b_full[NSTAGE]
+  static constexpr uint32_t SMEM = OFF_BAR + (N_BARS + 2) * 8;
 };
 
 template <int KC32, int TAPS, int N, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) k_conv(const ConvArgs a) {
   using Cfg = ConvCfg<KC32, TAPS, N, EPI>;
+  constexpr int NST = Cfg::NST;
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bar0 = sbase + Cfg::OFF_BAR;
-  // barriers: a_full[8] a_empty[8] acc_full[2] acc_empty[2] b_full[NSTAGE] b_empty[NSTAGE], then the TMEM base word
+  // barriers: a_full[8] a_empty[8] acc_full[2] acc_empty[2] b_full[NST] b_empty[NST], then the TMEM base word
   const uint32_t A_FULL = bar0, A_EMPTY = bar0 + 64, ACC_FULL = bar0 + 128, ACC_EMPTY = bar0 + 144, B_FULL = bar0 + 160,
-                 B_EMPTY = bar0 + 160 + NSTAGE * 8;
-  uint32_t* tmem_word = reinterpret_cast<uint32_t*>(smem + Cfg::OFF_BAR + 46 * 8);
+                 B_EMPTY = bar0 + 160 + NST * 8;
+  // cta_group::2, in the leader: the follower's A groups / weight halves have landed
+  const uint32_t PEER_A_FULL = bar0 + 160 + 2 * NST * 8, PEER_B_FULL = PEER_A_FULL + 64;
+  constexpr bool CTA2 = Cfg::CTA2;
+  uint32_t* tmem_word = reinterpret_cast<uint32_t*>(smem + Cfg::OFF_BAR + Cfg::N_BARS * 8);
   float* s_bias = reinterpret_cast<float*>(smem + Cfg::OFF_BIAS);
   float* s_vw = reinterpret_cast<float*>(smem + Cfg::OFF_VW);
 
@@ -130,14 +171,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) k_c
   const uint32_t pair0 = blockIdx.x >> 1, n_pairs_grid = gridDim.x >> 1, n_pair_tiles = (n_tiles + 1u) >> 1;
   if (threadIdx.x == 0) {
     for (int i = 0; i < 8; ++i) { mbar_init(A_FULL + i * 8, 1); mbar_init(A_EMPTY + i * 8, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(ACC_FULL + i * 8, 1); mbar_init(ACC_EMPTY + i * 8, 4); }
-    for (int i = 0; i < NSTAGE; ++i) { mbar_init(B_FULL + i * 8, 1); mbar_init(B_EMPTY + i * 8, 2); }   // empty: both CTAs' MMAs
+    for (int i = 0; i < 2; ++i) { mbar_init(ACC_FULL + i * 8, 1); mbar_init(ACC_EMPTY + i * 8, CTA2 ? 8 : 4); }   // cta2: both CTAs' epilogue warps
+    for (int i = 0; i < NST; ++i) { mbar_init(B_FULL + i * 8, 1); mbar_init(B_EMPTY + i * 8, CTA2 ? 1 : 2); }   // empty: both CTAs' MMAs / one pair commit
+    if (CTA2) {
+      for (int i = 0; i < 8; ++i) mbar_init(PEER_A_FULL + i * 8, 1);
+      for (int i = 0; i < NST; ++i) mbar_init(PEER_B_FULL + i * 8, 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int i = threadIdx.x; i < N; i += CONV_THREADS) s_bias[i] = a.bias[i];
   if (EPI == EPI_SKIP_RELU_VALUE)
     for (int i = threadIdx.x; i < N; i += CONV_THREADS) s_vw[i] = a.vw[i];
-  if (warp == 1) tmem_alloc(smem_u32(tmem_word), 512);
+  if (warp == 1) { if (CTA2) tmem_alloc2(smem_u32(tmem_word), 512); else tmem_alloc(smem_u32(tmem_word), 512); }
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();                                                // the peer's barriers exist before anything is sent to them
@@ -162,18 +207,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) k_c
             bulk_g2s(sbase + (uint32_t)(kc * 4 + c) * QA * 16, src + (size_t)(kc * 4 + c) * a.plane_rows * 16, QA * 16, A_FULL + kc * 8);
 #pragma unroll 1
           for (int tap = 0; tap < TAPS; ++tap, ++st) {
-            const uint32_t slot = st % NSTAGE;
-            mbar_wait_sleep(B_EMPTY + slot * 8, ((st / NSTAGE) & 1u) ^ 1u);      // both CTAs have read the slot's previous stage
-            mbar_expect_tx(B_FULL + slot * 8, Cfg::STAGE_BYTES);                 // own half + the peer's half
-            bulk_g2s_multicast(sbase + Cfg::OFF_B + slot * Cfg::STAGE_BYTES + rank * HALF,
-                               a.w + (size_t)(kc * TAPS + tap) * Cfg::STAGE_BYTES + rank * HALF, HALF, B_FULL + slot * 8, (uint16_t)3);
+            const uint32_t slot = st % NST;
+            // both CTAs have read the slot's previous stage (cta_group::2: slots are released four at a time)
+            if (!CTA2) mbar_wait_sleep(B_EMPTY + slot * 8, ((st / NST) & 1u) ^ 1u);
+            else if ((st & 3u) == 0u) mbar_wait_sleep(B_EMPTY + (slot >> 2) * 8, ((st / NST) & 1u) ^ 1u);
+            if (CTA2) {                                                          // this CTA's 128 B rows of the stage (packed contiguously)
+              mbar_expect_tx(B_FULL + slot * 8, HALF);
+              bulk_g2s(sbase + Cfg::OFF_B + slot * HALF, a.w + (size_t)(kc * TAPS + tap) * Cfg::STAGE_BYTES + rank * HALF, HALF, B_FULL + slot * 8);
+            } else {
+              mbar_expect_tx(B_FULL + slot * 8, Cfg::STAGE_BYTES);               // own half + the peer's half
+              bulk_g2s_multicast(sbase + Cfg::OFF_B + slot * Cfg::STAGE_BYTES + rank * HALF,
+                                 a.w + (size_t)(kc * TAPS + tap) * Cfg::STAGE_BYTES + rank * HALF, HALF, B_FULL + slot * 8, (uint16_t)3);
+            }
           }
         }
       }
       // the peer's last "slot is free" signals must have landed in THIS CTA's barriers before it exits
-      for (uint32_t k = 0; k < (uint32_t)NSTAGE && k < st; ++k) {
+      for (uint32_t k = 0; k < (uint32_t)NST && k < st; k += CTA2 ? 4u : 1u) {
         const uint32_t s2 = st - 1u - k;
-        mbar_wait_sleep(B_EMPTY + (s2 % NSTAGE) * 8, (s2 / NSTAGE) & 1u);
+        mbar_wait_sleep(B_EMPTY + (CTA2 ? (s2 % NST) >> 2 : s2 % NST) * 8, (s2 / NST) & 1u);
       }
     }
   } else if (warp == 1) {
@@ -181,43 +233,56 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) k_c
     const bool issuer = elect_one();
     constexpr uint32_t DESC_HI_A = 9u | (1u << 14);                 // A: SBO = 9 rows = 144 B between core matrices, descriptor version 1
     constexpr uint32_t DESC_HI_B = (128u >> 4) | (1u << 14);        // B: SBO = 128 B
-    constexpr uint32_t IDESC = make_idesc(N);
+    constexpr uint32_t IDESC = CTA2 ? make_idesc2(N) : make_idesc(N);
+    constexpr uint32_t NB = CTA2 ? N / 2 : N;                        // B rows in this CTA's shared memory
     // descriptor start addresses are CTA-relative 18-bit offsets: in a cluster the shared-window address of rank 1 carries
     // the CTA rank in its upper bits, which must not spill into the LBO field
     const uint32_t soff = sbase & 0x3FFFFu;
     const uint32_t a_lo_base = ((soff >> 4) + 16u) | ((uint32_t)QA << 16);   // row 16 of the buffer, LBO = QA rows
+    const bool leader = !CTA2 || rank == 0;
     uint32_t it = 0, st = 0;
     for (uint32_t pt = pair0; pt < n_pair_tiles; pt += n_pairs_grid, ++it) {
       const uint32_t buf = it & 1u, par = (it >> 1) & 1u;
-      mbar_wait(ACC_EMPTY + buf * 8, par ^ 1u);
-      tc_fence_after();
+      if (leader) {
+        mbar_wait(ACC_EMPTY + buf * 8, par ^ 1u);
+        tc_fence_after();
+      }
       const uint32_t d_tmem = tmem_base + buf * 256;
 #pragma unroll 1
       for (int kc = 0; kc < KC32; ++kc) {
         mbar_wait(A_FULL + kc * 8, it & 1u);
+        if (CTA2 && leader) mbar_wait(PEER_A_FULL + kc * 8, it & 1u);
+        if (CTA2 && !leader && issuer) mbar_arrive_cluster(mapa_shared(PEER_A_FULL + kc * 8, 0));   // my A group has landed
         tc_fence_after();
 #pragma unroll 1
         for (int tap = 0; tap < TAPS; ++tap, ++st) {
           const int shift = TAPS == 9 ? (tap / 3 - 1) * 9 + (tap % 3 - 1) : 0;
-          const uint32_t slot = st % NSTAGE;
-          mbar_wait(B_FULL + slot * 8, (st / NSTAGE) & 1u);
+          const uint32_t slot = st % NST;
+          mbar_wait(B_FULL + slot * 8, (st / NST) & 1u);
+          // the follower forwards its weight halves four stages at a time (a remote arrival per stage would bound the loop)
+          if (CTA2 && leader && (st & 3u) == 0u) mbar_wait(PEER_B_FULL + (slot >> 2) * 8, (st / NST) & 1u);
+          if (CTA2 && !leader && issuer && (st & 3u) == 3u) mbar_arrive_cluster(mapa_shared(PEER_B_FULL + (slot >> 2) * 8, 0));
           tc_fence_after();
-          if (issuer) {
-            const uint32_t b_lo_base = ((soff + Cfg::OFF_B + slot * Cfg::STAGE_BYTES) >> 4) | ((uint32_t)N << 16);
+          if (issuer && leader) {
+            const uint32_t b_lo_base = ((soff + Cfg::OFF_B + slot * Cfg::SLOT_BYTES_B) >> 4) | ((uint32_t)NB << 16);
 #pragma unroll
             for (int kk = 0; kk < 2; ++kk) {
               const uint32_t a_lo = a_lo_base + (uint32_t)(shift + (kc * 4 + kk * 2) * QA);
-              const uint32_t b_lo = b_lo_base + (uint32_t)(kk * 2 * N);
-              umma_f16(d_tmem, ((uint64_t)DESC_HI_A << 32) | a_lo, ((uint64_t)DESC_HI_B << 32) | b_lo, IDESC, (tap | kc | kk) != 0);
+              const uint32_t b_lo = b_lo_base + (uint32_t)(kk * 2 * NB);
+              if (CTA2) umma2_f16(d_tmem, ((uint64_t)DESC_HI_A << 32) | a_lo, ((uint64_t)DESC_HI_B << 32) | b_lo, IDESC, (tap | kc | kk) != 0);
+              else umma_f16(d_tmem, ((uint64_t)DESC_HI_A << 32) | a_lo, ((uint64_t)DESC_HI_B << 32) | b_lo, IDESC, (tap | kc | kk) != 0);
             }
-            umma_commit_multicast(B_EMPTY + slot * 8, (uint16_t)3);   // frees the slot in both CTAs
+            if (!CTA2) umma_commit_multicast(B_EMPTY + slot * 8, (uint16_t)3);   // frees the slot in both CTAs
+            else if ((st & 3u) == 3u) umma2_commit_multicast(B_EMPTY + (slot >> 2) * 8, (uint16_t)3);   // ... four slots
           }
           __syncwarp();
         }
-        if (issuer) umma_commit(A_EMPTY + kc * 8);                  // this channel group of the A tile has been read
+        if (issuer && leader) {                                       // this channel group of the A tile has been read
+          if (CTA2) umma2_commit_multicast(A_EMPTY + kc * 8, (uint16_t)3); else umma_commit(A_EMPTY + kc * 8);
+        }
         __syncwarp();
       }
-      if (issuer) umma_commit(ACC_FULL + buf * 8);
+      if (issuer && leader) { if (CTA2) umma2_commit_multicast(ACC_FULL + buf * 8, (uint16_t)3); else umma_commit(ACC_FULL + buf * 8); }
       __syncwarp();
     }
   } else {
@@ -294,14 +359,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) k_c
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(ACC_EMPTY + buf * 8);
+      if (lane == 0) {                                                // cta_group::2: the leader's barrier collects both CTAs' epilogue warps
+        if (CTA2 && rank != 0) mbar_arrive_cluster(mapa_shared(ACC_EMPTY + buf * 8, 0)); else mbar_arrive(ACC_EMPTY + buf * 8);
+      }
     }
   }
   tc_fence_before();
   __syncwarp();
   __syncthreads();
   cluster_sync_all();                                                // no CTA leaves while its peer may still signal its barriers
-  if (warp == 1) tmem_dealloc(tmem_base, 512);
+  if (warp == 1) { if (CTA2) tmem_dealloc2(tmem_base, 512); else tmem_dealloc(tmem_base, 512); }
 }
 
 // ---- input planes (get_encoding, chess.rs:176-249) as the stem's A operand: [4 chunks][rows][8] bf16 ------------------
@@ -406,8 +473,11 @@ static inline uint16_t f2bf(float f) {
 }
 
 // weight stages of one conv: [kc32][tap][4 chunks][N][8] bf16; input channels padded to kc32*32, outputs to N
+// cta_group::2 convolutions: a stage is two halves [rank][4 chunks][N/2][8], rank r = output channels r N/2 .. (r+1) N/2 - 1
 static void pack_conv(const HostNet::Conv& cv, int kc32, int N, uint16_t* dst) {
   const int taps = cv.k * cv.k;
+  const bool halves = conv_cta2(kc32, taps, N);
+  const int NH = halves ? N / 2 : N;
   for (int tap = 0; tap < taps; ++tap)
     for (int kc = 0; kc < kc32; ++kc) {
       uint16_t* st = dst + ((size_t)kc * taps + tap) * 4 * N * 8;
@@ -415,7 +485,7 @@ static void pack_conv(const HostNet::Conv& cv, int kc32, int N, uint16_t* dst) {
         for (int kl = 0; kl < 32; ++kl) {
           const int k = kc * 32 + kl;
           const float w = (n < cv.oc && k < cv.ic) ? cv.w[((size_t)n * cv.ic + k) * taps + tap] : 0.0f;
-          st[((size_t)(kl / 8) * N + n) * 8 + (kl % 8)] = f2bf(w);
+          st[(size_t)(n / NH) * 4 * NH * 8 + ((size_t)(kl / 8) * NH + (n % NH)) * 8 + (kl % 8)] = f2bf(w);
         }
     }
 }
