@@ -558,25 +558,31 @@ int32_t spb_chess_search(spb_chess_engine* e, uint32_t num_searches) {
       CH_CUDA(e, cudaEventRecord(e->ev_fork, e->stream));
       CH_CUDA(e, cudaStreamWaitEvent(e->stream2, e->ev_fork, 0));
     }
-    for (uint32_t s = 0; s < num_searches; ++s) {
-      for (int h = 0; h < nh; ++h) {
-        const ch::TreeRange& R = half[h];
-        const uint32_t hb = (R.g1 - R.g0 + ch::WARPS - 1) / ch::WARPS;
-        CH_CUDA(e, cudaMemsetAsync(R.count, 0, 4, st[h]));
-        ch::k_chess_select<<<hb, ch::THREADS, 0, st[h]>>>(e->T, R);
-        CH_CUDA(e, cudaGetLastError());
-        uint32_t launched = 0;
-        const int32_t rc = ch::net_forward_leaves(e, h, R.list, R.count, st[h], &launched);
-        if (rc) return rc;
-        ch::k_chess_finish<false><<<hb, ch::THREADS, 0, st[h]>>>(e->T, R);
-        CH_CUDA(e, cudaGetLastError());
-        e->launches += 2 + launched;
+    auto enqueue = [&]() -> int32_t {
+      for (uint32_t s = 0; s < num_searches; ++s) {
+        for (int h = 0; h < nh; ++h) {
+          const ch::TreeRange& R = half[h];
+          const uint32_t hb = (R.g1 - R.g0 + ch::WARPS - 1) / ch::WARPS;
+          CH_CUDA(e, cudaMemsetAsync(R.count, 0, 4, st[h]));
+          ch::k_chess_select<<<hb, ch::THREADS, 0, st[h]>>>(e->T, R);
+          CH_CUDA(e, cudaGetLastError());
+          uint32_t launched = 0;
+          const int32_t rc = ch::net_forward_leaves(e, h, R.list, R.count, st[h], &launched);
+          if (rc) return rc;
+          ch::k_chess_finish<false><<<hb, ch::THREADS, 0, st[h]>>>(e->T, R);
+          CH_CUDA(e, cudaGetLastError());
+          e->launches += 2 + launched;
+        }
       }
+      return SPB_OK;
+    };
+    const int32_t rc_loop = enqueue();
+    if (split) {                                                       // the second stream rejoins the engine's stream, also after an error
+      cudaError_t je = cudaEventRecord(e->ev_join, e->stream2);
+      if (je == cudaSuccess) je = cudaStreamWaitEvent(e->stream, e->ev_join, 0);
+      if (je != cudaSuccess && rc_loop == SPB_OK) { e->set_error(std::string("chess search: ") + cudaGetErrorString(je)); return SPB_ERR_CUDA; }
     }
-    if (split) {
-      CH_CUDA(e, cudaEventRecord(e->ev_join, e->stream2));
-      CH_CUDA(e, cudaStreamWaitEvent(e->stream, e->ev_join, 0));
-    }
+    if (rc_loop) return rc_loop;
   } else if (e->cfg.flags & SPB_FLAG_FORCE_SPLIT) {
     // parity harness: the built-in evaluators through the kernels of the network pipeline (select -> evaluate -> finish)
     for (uint32_t s = 0; s < num_searches; ++s) {
