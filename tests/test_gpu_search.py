@@ -339,3 +339,17 @@ def test_gather_over_the_c_abi_with_one_rank_equals_drain():
     enc, pol, val = S.positions_to_training(S.GAME_C4, pos)
     assert enc.shape == (len(pos), 3, 6, 7) and np.allclose(pol.sum(1), 1.0) and set(np.unique(val)) <= {-1.0, 0.0, 1.0}
     assert np.array_equal(enc[:, 2], 1.0 - enc[:, 0] - enc[:, 1])
+
+
+@pytest.mark.gpu
+def test_root_children_all_writes_into_caller_buffers():
+    """bench.py's end-to-end steps hand page-locked arrays to root_children_all(out=...): same numbers as a fresh call."""
+    with S.Engine(game=S.GAME_C4, num_games=16, evaluator=S.EVAL_DET) as e:
+        e.reset_games()
+        e.search(50)
+        fresh = e.root_children_all()
+        bufs = tuple(np.full_like(x, 0xFF) for x in fresh)
+        got = e.root_children_all(bufs)
+        assert all(g is b for g, b in zip(got, bufs))
+        for g, f in zip(got, fresh):
+            assert (g == f).all()
