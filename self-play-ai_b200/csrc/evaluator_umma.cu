@@ -235,11 +235,20 @@ static_assert(Smem<Connect4>::TOTAL <= 232448 && Smem<TicTacToe>::TOTAL <= 23244
 constexpr int PRODUCER_WARP = 0, MMA_WARP = 1, STAGER_WARP = 2, SPARE_WARP = 3;   // warp 3: publisher of the results
 constexpr int EPI_WARP0 = 4, N_EPI_WARPS = 8;
 constexpr int THREADS = 32 * (EPI_WARP0 + N_EPI_WARPS);   // 384: static work list (spb_predict, lock-step pipeline)
-constexpr int TREE_WARPS = 4;    // asynchronous pipeline: warps 12..15 (warpgroup 3),: tree warps that share the CTA (and the SM's idle issue slots)
-constexpr int THREADS_RING = THREADS + 32 * TREE_WARPS;   // 512 = 4 warpgroups x 128 registers = the whole register file
+// asynchronous pipeline: tree warps that share the CTA (and the SM's idle issue slots): warps 12..15 (one warpgroup), 512
+// threads = 4 warpgroups x 128 registers = the whole register file.  setmaxnreg moves registers inside what the CTA was given
+// at launch (threads x registers per thread): the budgets of a configuration must sum to at most that, not to the register
+// file (a tic-tac-toe configuration with 8 tree warps, 640 threads x 96 registers, hung at 72 / 144 / 64 = 62,464 > 61,440 and
+// ran 18 % slower than this one at 72 / 136 / 64: the tree code spills at 64 registers).
+template <class G> struct RingCfg { static constexpr int TREE_WARPS = 4, REGS_LAUNCH = 128, REGS_LIGHT = 72, REGS_TREE = 96, REGS_EPILOGUE = 168; };
+template <class G> constexpr int threads_ring() { return THREADS + 32 * RingCfg<G>::TREE_WARPS; }
+template <class G> constexpr bool ring_budget_ok() {
+  return 128 * RingCfg<G>::REGS_LIGHT + 256 * RingCfg<G>::REGS_EPILOGUE + 32 * RingCfg<G>::TREE_WARPS * RingCfg<G>::REGS_TREE <= threads_ring<G>() * RingCfg<G>::REGS_LAUNCH &&
+         threads_ring<G>() * RingCfg<G>::REGS_LAUNCH <= 65536;
+}
+static_assert(ring_budget_ok<Connect4>() && ring_budget_ok<TicTacToe>(), "setmaxnreg budget exceeds the CTA's launch allocation");
 // setmaxnreg budget of the asynchronous kernel: warpgroup 0 (producer, MMA issuer, stager, one idle warp) and warpgroup 3
 // (tree warps) give registers to warpgroups 1 and 2 (epilogue): 128 x 72 + 128 x 96 + 256 x 168 = 64,512 <= 65,536.
-constexpr int REGS_LIGHT = 72, REGS_TREE = 96, REGS_EPILOGUE = 168;
 constexpr uint32_t CLAIM_GRACE_NS = 4000;   // a batch waits this long for tickets behind its first filled one
 
 // Static work source (spb_predict, lock-step pipeline).  The asynchronous pipeline reads T.leaf_state / writes T.eval_out.
@@ -274,7 +283,7 @@ __device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; a
 #endif
 
 template <class G, bool RING>
-__global__ void __launch_bounds__(RING ? THREADS_RING : THREADS, 1)
+__global__ void __launch_bounds__(RING ? threads_ring<G>() : THREADS, 1)
 k_eval_umma(const uint8_t* __restrict__ image, const EvalWork W, const Trees T, const AsyncCtl C) {
   using Ge = Geo<G>;
   using Sm = Smem<G>;
@@ -366,9 +375,9 @@ k_eval_umma(const uint8_t* __restrict__ image, const EvalWork W, const Trees T, 
   // Asynchronous kernel: register reallocation by whole warpgroups (setmaxnreg), first thing in every role's branch so
   // that the role's code is compiled for its own budget: the epilogue warps hold two accumulator halves, the skip
   // connection and the layer's biases in registers; the other roles are light.
-#define SPB_REGS_LIGHT() do { if (RING) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_LIGHT)); } while (0)
-#define SPB_REGS_TREE() do { if (RING) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_TREE)); } while (0)
-#define SPB_REGS_EPILOGUE() do { if (RING) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_EPILOGUE)); } while (0)
+#define SPB_REGS_LIGHT() do { if (RING) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(RingCfg<G>::REGS_LIGHT)); } while (0)
+#define SPB_REGS_TREE() do { if (RING) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(RingCfg<G>::REGS_TREE)); } while (0)
+#define SPB_REGS_EPILOGUE() do { if (RING) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(RingCfg<G>::REGS_EPILOGUE)); } while (0)
 
   if (warp == PRODUCER_WARP) {
     // ===== weight producer: streams the layers' kernel-row blocks into the 3-group ring ==================
@@ -976,7 +985,7 @@ static cudaError_t launch_ring_t(const Evaluator::DevNet& net, const Trees& T, c
   cudaError_t e = prepare<G, true>(&sm_count);
   if (e != cudaSuccess) return e;
   const unsigned grid = (unsigned)std::max(1, std::min<int>(sm_count, (int)T.G));
-  k_eval_umma<G, true><<<grid, THREADS_RING, Smem<G>::TOTAL, stream>>>(reinterpret_cast<const uint8_t*>(net.w_umma), EvalWork{}, T, C);
+  k_eval_umma<G, true><<<grid, threads_ring<G>(), Smem<G>::TOTAL, stream>>>(reinterpret_cast<const uint8_t*>(net.w_umma), EvalWork{}, T, C);
   return cudaGetLastError();
 }
 
